@@ -1,0 +1,194 @@
+"""CPU: the oracle ports against the fixtures generated from the real
+reference (oracle/make_golden.py), and -- when /root/reference is mounted --
+against the reference itself."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_port as P
+from oracle import spars_port as SP
+from oracle.make_golden import loss_config, make_inputs
+from oracle.ref_shim import reference_available
+
+from conftest import GOLDEN
+
+LOSS_CASES = {
+    'l1_default': loss_config('l1'),
+    'bayesian_default': loss_config('bayesian'),
+    'log_bayesian_scale1': loss_config('log_bayesian'),
+    'l1_allterms': loss_config('l1', smoothness_weight=0.6,
+                               consistency_weight=0.8),
+    'bayesian_pooling': loss_config('bayesian', smoothness_weight=0.6,
+                                    consistency_weight=0.8, pooling=True),
+    'bayesian_smooth': loss_config('bayesian'),
+}
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+@pytest.mark.parametrize('name', sorted(LOSS_CASES))
+@pytest.mark.parametrize('tag', ['f32', 'f64'])
+def test_loss_port_matches_reference_fixture(name, tag):
+    g = load(f'loss_{name}.npz')
+    dt = torch.float32 if tag == 'f32' else torch.float64
+    stereo = torch.cat([torch.from_numpy(g['left']),
+                        torch.from_numpy(g['right'])], 1).to(dt)
+    preds = [torch.from_numpy(g[f'pred{i}']).to(dt) for i in range(4)]
+    dl, el, grads = P.step(stereo, preds, LOSS_CASES[name])
+    # same ATen ops in the same order -> identical up to reduction order
+    tol = 1e-6 if tag == 'f32' else 1e-12
+    assert abs(float(dl) - float(g[f'disp_loss_{tag}'])) \
+        <= tol * abs(float(g[f'disp_loss_{tag}']))
+    assert abs(float(el) - float(g[f'error_loss_{tag}'])) \
+        <= tol * abs(float(g[f'error_loss_{tag}']))
+    for i in range(4):
+        ref = g[f'grad{i}_{tag}']
+        assert np.allclose(grads[i].numpy(), ref, rtol=0,
+                           atol=tol * 10 * np.abs(ref).max())
+    if tag == 'f32':
+        pyr = P.pyramid(stereo, 4)
+        rec = P.recon_pyramid(preds, pyr)
+        for i in range(4):
+            assert np.array_equal(pyr[i].numpy(), g[f'pyr{i}_f32'])
+            assert np.array_equal(rec[i].numpy(), g[f'rec{i}_f32'])
+            err = P.image_error(pyr[i], rec[i])
+            assert np.allclose(err.numpy(), g[f'err{i}_f32'], atol=1e-7)
+
+
+def test_component_ports_match_reference_fixture():
+    g = load('components.npz')
+    for tag, dt, tol in (('f32', torch.float32, 2e-6),
+                         ('f64', torch.float64, 1e-12)):
+        im = torch.from_numpy(g['images']).to(dt)
+        rc = torch.from_numpy(g['recon']).to(dt).requires_grad_(True)
+        pr = torch.from_numpy(g['pred']).to(dt).requires_grad_(True)
+        er = torch.from_numpy(g['error']).to(dt)
+
+        def check(val, wrt, key):
+            grad, = torch.autograd.grad(val, wrt)
+            assert np.allclose(val.detach().numpy(), g[f'{key}_{tag}'],
+                               rtol=tol, atol=0), key
+            ref = g[f'{key}_grad_{tag}']
+            assert np.allclose(grad.numpy(), ref, rtol=0,
+                               atol=10 * tol * np.abs(ref).max()), key
+
+        for alpha in (0.85, 1.0):
+            e = P.image_error(im, rc, alpha)
+            assert np.allclose(e.detach().numpy(),
+                               g[f'image_error_a{alpha}_{tag}'], atol=tol)
+            check((e[:, 0:1] + e[:, 1:2]).mean(), rc, f'wssim_a{alpha}')
+        check(P.consistency(pr[:, 0:2]), pr, 'cons')
+        check(P.consistency(pr[:, 2:4], pr[:, 0:2]), pr, 'cons_ab')
+        check(P.smoothness(pr[:, 0:2], im), pr, 'smooth')
+        for lt in P.LOSS_TYPES:
+            for pooling in (False, True):
+                key = f'reproj_{lt}_{"pool" if pooling else "nopool"}'
+                check(P.uncertainty_loss(pr, im, er, lt, 0.7, 0.3, pooling),
+                      pr, key)
+        assert np.allclose(P.warp_to_left(pr[:, 0:1].detach(), im[:, 3:6]),
+                           g[f'recon_left_{tag}'], atol=tol)
+        assert np.allclose(P.warp_to_right(pr[:, 1:2].detach(), im[:, 0:3]),
+                           g[f'recon_right_{tag}'], atol=tol)
+
+
+def test_loss_type_validation():
+    with pytest.raises(ValueError, match='Loss must be either'):
+        P.uncertainty_loss(torch.rand(1, 4, 8, 8), torch.rand(1, 6, 8, 8),
+                           torch.rand(1, 2, 8, 8), loss_type='l2')
+
+
+def test_anchor_c1_full_size():
+    """Appendix C / anchors.npz: config-1 shape, seed 0, reference fp32."""
+    g = load('anchors.npz')
+    b, h, w = g['c1_shape']
+    left, right, preds = make_inputs(int(b), int(h), int(w), 0.3, 0)
+    dl, el, grads = P.step(torch.cat([left, right], 1), preds,
+                           loss_config('l1'))
+    assert abs(float(dl) - float(g['c1_disp_loss'])) < 1e-5
+    assert abs(float(el) - float(g['c1_error_loss'])) < 1e-5
+    l2 = np.array([float(x.double().norm()) for x in grads])
+    assert np.allclose(l2, g['c1_grad_l2'], rtol=1e-5)
+
+
+# ---------------------------------------------------------------- spars ----
+def test_pool_exact_is_bit_identical_to_aten():
+    g = load('spars.npz')
+    for name in ('small', 'ties', 'ragged'):
+        for m in ('err', 'unc'):
+            mine = SP.pool_exact(g[f'{name}_{m}'], 11)
+            assert np.array_equal(mine, g[f'{name}_pooled_{m}']), (name, m)
+
+
+def test_stable_order_matches_torch_stable_argsort():
+    g = load('spars.npz')
+    for name in ('small', 'ties', 'ragged'):
+        p = SP.pool_exact(g[f'{name}_unc'], 11)
+        rows = p.shape[0] * 2
+        order = SP.stable_order(p.reshape(rows, -1))
+        assert np.array_equal(order.reshape(p.shape[0], 2, -1),
+                              g[f'{name}_stable_order_unc']), name
+
+
+def test_curves_match_reference_fixture():
+    g = load('spars.npz')
+    for name in ('small', 'ties', 'ragged'):
+        err, unc = g[f'{name}_err'], g[f'{name}_unc']
+        oc = SP.curve_canonical(err, err)
+        pc = SP.curve_canonical(err, unc)
+        # the reference sums in fp32 in ATen's order: 1e-6 relative
+        assert np.allclose(oc, g[f'{name}_oracle_curve'], rtol=2e-6, atol=0)
+        if name != 'ties':   # unstable argsort in the reference on ties
+            assert np.allclose(pc, g[f'{name}_pred_curve'], rtol=2e-6, atol=0)
+            assert abs(float(SP.ause_canonical(oc, pc))
+                       - float(g[f'{name}_ause'])) < 1e-6
+        t_oc = SP.curve_reference_style(torch.from_numpy(err),
+                                        torch.from_numpy(err))
+        t_pc = SP.curve_reference_style(torch.from_numpy(err),
+                                        torch.from_numpy(unc))
+        assert np.allclose(t_oc.numpy(), g[f'{name}_oracle_curve'],
+                           rtol=1e-6)
+        assert np.allclose(t_pc.numpy(), pc, rtol=2e-6)
+
+
+def test_ause_length_check():
+    with pytest.raises(Exception, match='different step sizes'):
+        SP.ause_canonical(np.zeros(3, np.float32), np.zeros(4, np.float32))
+    with pytest.raises(Exception, match='different step sizes'):
+        SP.ause_reference_style(torch.zeros(3), torch.zeros(4))
+
+
+def test_cut_points_follow_the_float_formula():
+    """sparsification.py:26-27 uses Python float arithmetic; it is NOT always
+    step*N//100 (e.g. N=1380), so the host computes the cuts the same way."""
+    n = (1024 - 10) * (1280 - 10)
+    cuts = SP.cut_points(n)
+    assert all(int(cuts[s]) == s * n // 100 for s in range(100))
+    for h, w in ((256, 512), (192, 384), (40, 56), (23, 31)):
+        n = (h - 10) * (w - 10)
+        cuts = SP.cut_points(n)
+        assert all(int(cuts[s]) == int(s / 100 * n) for s in range(100))
+        assert cuts[-1] == n and np.all(np.diff(cuts) >= 0)
+
+
+@pytest.mark.skipif(not reference_available(),
+                    reason='reference tree not mounted')
+def test_port_against_live_reference():
+    from oracle.ref_shim import import_reference
+    L, u, S = import_reference()
+    left, right, preds = make_inputs(1, 24, 40, 0.7, 9)
+    stereo = torch.cat([left, right], 1)
+    cfg = loss_config('bayesian', smoothness_weight=0.3)
+    dl, el, grads = P.step(stereo, preds, cfg)
+    pr = [p.clone().requires_grad_(True) for p in preds]
+    pyr = u.scale_pyramid(stereo, 4)
+    rdl, rel = L.TukraUncertaintyLoss(**cfg)(
+        pyr, pr, u.reconstruct_pyramid(pr, pyr), 0, None)
+    (rdl + rel).backward()
+    assert float(dl) == pytest.approx(float(rdl), rel=1e-6)
+    assert float(el) == pytest.approx(float(rel), rel=1e-6)
+    for a, b in zip(grads, pr):
+        assert torch.allclose(a, b.grad, atol=1e-7)
