@@ -1,0 +1,172 @@
+/* libusl.so -- C ABI of the B200-native stereo-uncertainty loss path.
+ *
+ * This is the drop-in boundary.  The reference (Probabilistic-Surgical-Vision/
+ * uncertainty-model) is pure Python on top of ATen and has no FFI of its own;
+ * each entry point below replaces the ATen call sequence of one reference
+ * function (cited as file:line under /root/reference) and is bound from Python
+ * with ctypes (uncertainty_model_b200/_lib.py; the stub a reference maintainer
+ * would add is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 (unless stated), owned by the
+ *     caller (PyTorch's allocator); the library never allocates, frees or
+ *     retains caller memory;
+ *   - image-like tensors are NCHW with contiguous h*w planes; `*_bs` / `*_cs`
+ *     are the batch / channel strides in elements, so channel slices of a
+ *     larger tensor (prediction[:, :2]) are passed without a copy;
+ *   - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises
+ *     the host;
+ *   - return value: USL_OK or a negative UslError; never throws, never exits.
+ *   - re-entrant: no global mutable state.
+ */
+#ifndef USL_H_
+#define USL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USL_VERSION 100
+#define USL_MAX_SCALES 8
+#define USL_NUM_TERMS 6
+
+typedef enum UslError {
+    USL_OK = 0,
+    USL_ERR_ARG = -1,         /* null pointer / non-positive size / bad enum */
+    USL_ERR_CUDA = -2,        /* launch failed (cudaGetLastError) */
+    USL_ERR_UNSUPPORTED = -3, /* shape outside what the kernels handle */
+    USL_ERR_WORKSPACE = -4    /* workspace too small */
+} UslError;
+
+int usl_version(void);
+const char* usl_strerror(int rc);
+
+/* ---- train/utils.py:27-50  scale_pyramid ---------------------------------
+ * src (B,C,H,W).  dst[i], i = 1..scales-1, contiguous (B,C,H>>i,W>>i);
+ * dst[0] is ignored (level 0 is the input itself, aliased by the host). */
+int usl_pyramid(const float* src, int B, int C, int H, int W, long long src_bs,
+                long long src_cs, int scales, float* const* dst, void* stream);
+
+/* ---- train/utils.py:65-109  reconstruct / reconstruct_{left,right}_image --
+ * out[b,c] = grid_sample(image[b,c], base + sign*disp[b]) ; sign = -1 for the
+ * left reconstruction, +1 for the right one. */
+int usl_warp_fwd(const float* disp, long long disp_bs, float sign,
+                 const float* image, long long img_bs, long long img_cs, int B,
+                 int C, int h, int w, float* out, long long out_bs,
+                 long long out_cs, void* stream);
+/* gradient of the above w.r.t. disp (gather; deterministic). */
+int usl_warp_bwd_disp(const float* disp, long long disp_bs, float sign,
+                      const float* image, long long img_bs, long long img_cs,
+                      const float* grad_out, long long go_bs, long long go_cs,
+                      int B, int C, int h, int w, float* grad_disp,
+                      long long gd_bs, void* stream);
+
+/* ---- train/loss.py  fused per-scale loss ----------------------------------
+ * Term bits (UslLossConfig.terms) and the index of their raw sum in `sums`: */
+#define USL_TERM_REPROJ 1u   /* [0] WeightedSSIMLoss            loss.py:133-151 */
+#define USL_TERM_CONS_D 2u   /* [1] ConsistencyLoss(disp)       loss.py:167-188 */
+#define USL_TERM_SMOOTH_D 4u /* [2] SmoothnessLoss(disp, img)   loss.py:248-264 */
+#define USL_TERM_UNC 8u      /* [3] l1|bayesian|log_bayesian    loss.py:389-403 */
+#define USL_TERM_SMOOTH_U 16u/* [4] SmoothnessLoss(unc, img)    loss.py:428-429 */
+#define USL_TERM_CONS_U 32u  /* [5] ConsistencyLoss(unc, disp)  loss.py:430-431 */
+
+#define USL_LOSS_L1 0
+#define USL_LOSS_BAYESIAN 1
+#define USL_LOSS_LOG_BAYESIAN 2
+
+typedef struct UslLossConfig {
+    uint32_t terms;
+    int32_t loss_type;          /* USL_LOSS_*  (loss.py:364-375) */
+    float alpha, c1, c2;        /* loss.py:30-32 (c1 = k1^2, c2 = k2^2) */
+    /* loss contribution of raw sum k is coef[k] * sums[k]: the host folds the
+     * config weights (loss.py:560-566), 1/N means and the 1/2^i of
+     * loss.py:546 into it.  Terms 0-2 feed output 0 (disparity loss), terms
+     * 3-5 output 1 (error loss). */
+    float coef[USL_NUM_TERMS];
+} UslLossConfig;
+
+typedef struct UslLossScale {
+    int32_t B, h, w;
+    int32_t reserved;
+    const float* images;  int64_t img_bs, img_cs;    /* (B,6,h,w) L_rgb,R_rgb */
+    const float* disp;    int64_t disp_bs, disp_cs;  /* (B,2,h,w) d_L,d_R     */
+    const float* unc;     int64_t unc_bs, unc_cs;    /* (B,2,h,w) u_L,u_R     */
+    const float* recon_in; int64_t rin_bs, rin_cs;   /* optional (B,6,h,w): use
+                              this reconstruction instead of warping in-kernel */
+    const float* err_in;  int64_t ein_bs, ein_cs;    /* optional (B,2,h,w): use
+                              this error map (ReprojectionErrorLoss stand-alone) */
+    float* recon_out;            /* optional, contiguous (B,6,h,w) [forward]  */
+    float* err_out;              /* optional, contiguous (B,2,h,w) [forward]  */
+    const float* grad_recon_in;  /* optional, contiguous (B,6,h,w) [backward]:
+                              extra dL/d(recon_out), e.g. from a discriminator */
+    float* grad_disp;     int64_t gd_bs, gd_cs;      /* (B,2,h,w) [backward]  */
+    float* grad_unc;      int64_t gu_bs, gu_cs;      /* (B,2,h,w) [backward]  */
+    float* grad_recon_out;       /* contiguous (B,6,h,w) [backward, recon_in] */
+} UslLossScale;
+
+/* All pyramid scales of a step are processed by ONE launch: `cfgs` and
+ * `scales` are HOST arrays of n_scales entries (largest scale first).
+ *
+ * number of CTAs (= rows of `partials`, USL_NUM_TERMS floats each) the forward
+ * launch uses for one scale; <0 on error. */
+int usl_loss_fwd_ctas(const UslLossScale* s);
+/* forward: per-CTA partial sums of the enabled terms -> partials (scale-major,
+ * scale i starting at row sum_{j<i} usl_loss_fwd_ctas(scales[j])). */
+int usl_loss_fwd(const UslLossConfig* cfgs, const UslLossScale* scales,
+                 int n_scales, float* partials, void* stream);
+/* fixed-order fp64 reduction of the partials -> sums[n_scales][6] (device).
+ * cta_starts: HOST array of n_scales+1 row offsets into `partials`. */
+int usl_loss_reduce(const float* partials, const int* cta_starts, int n_scales,
+                    double* sums, void* stream);
+/* *out_disp = sum_s sum_{k<3} coef[s][k]*sums[s][k]; *out_err likewise for
+ * k>=3.  All device pointers (coef: fp32 [n_scales][6]). */
+int usl_loss_combine(const double* sums, const float* coef, int n_scales,
+                     float* out_disp, float* out_err, void* stream);
+/* backward: gout_* = device scalars, the upstream gradients of the two
+ * outputs (NULL = that output does not take part in the backward).  Writes
+ * grad_disp / grad_unc (and grad_recon_out when recon_in is given) of every
+ * scale.  Two launches: the deterministic transposed warp of the consistency
+ * terms, then the fused stencil backward. */
+int usl_loss_bwd(const UslLossConfig* cfgs, const UslLossScale* scales,
+                 int n_scales, const float* gout_disp, const float* gout_err,
+                 int stages, void* stream);
+/* `stages`: which of the two backward launches to enqueue (both for a real
+ * backward; bench.py times them one at a time). */
+#define USL_BWD_STAGE_SCATTER 1
+#define USL_BWD_STAGE_MAIN 2
+#define USL_BWD_STAGE_ALL 3
+
+/* 3x3 valid mean (loss.py:386-387, `pooling=True`) and its transpose. */
+int usl_pool3_fwd(const float* x, long long x_bs, long long x_cs, int B, int C,
+                  int h, int w, float* out, void* stream);
+int usl_pool3_bwd(const float* grad_out, int B, int C, int h, int w,
+                  float* grad_x, void* stream);
+
+/* ---- train/sparsification.py  curve / ause --------------------------------
+ * rows = frames*2 maps of (H,W); k = pooling kernel; n = (H-k+1)*(W-k+1). */
+#define USL_MAX_STEPS 512
+#define USL_SPARS_MAX_KERNEL 15
+size_t usl_spars_workspace_bytes(int rows, int H, int W, int k, int with_order);
+/* cuts: HOST array of steps+1 ints, removed_k then n (sparsification.py:26-27).
+ * row_norm_sum: device fp64[steps], sum over rows of the normalised tail means.
+ * order_out: optional device int32[rows*n], the stable descending permutation
+ * of the pooled predicted error; pooled_*_out optional device fp32[rows*n]. */
+int usl_spars_curve(const float* oracle, const float* predicted, int rows,
+                    int H, int W, int k, const int* cuts, int steps,
+                    double* row_norm_sum, int32_t* order_out,
+                    float* pooled_oracle_out, float* pooled_pred_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* curve[k] = fp32(row_norm_sum[k] / total_rows)  (sparsification.py:32-36). */
+int usl_spars_finish(const double* row_norm_sum, int steps, long long total_rows,
+                     float* curve, void* stream);
+/* sparsification.py:46-57: fp32( sum_k fp32(pred_k - oracle_k) / steps ). */
+int usl_spars_ause(const float* oracle_curve, const float* pred_curve,
+                   int steps, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USL_H_ */

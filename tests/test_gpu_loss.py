@@ -1,0 +1,388 @@
+"""GPU parity tests of the loss path: the CUDA kernels (through the drop-in
+classes, i.e. through the C ABI) against the golden fixtures generated from the
+real reference and against the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): loss 1e-5 relative, gradients 1e-4
+relative (norm-wise, against the fp64 run of the reference/oracle)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+LOSS_REL = 1e-5
+GRAD_REL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from uncertainty_model_b200 import _lib
+    _lib.lib()      # must be the in-tree libusl.so; raises if missing
+    return torch.device('cuda:0')
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def cases():
+    from oracle.make_golden import loss_config
+    return {
+        'l1_default': loss_config('l1'),
+        'bayesian_default': loss_config('bayesian'),
+        'log_bayesian_scale1': loss_config('log_bayesian'),
+        'l1_allterms': loss_config('l1', smoothness_weight=0.6,
+                                   consistency_weight=0.8),
+        'bayesian_pooling': loss_config('bayesian', smoothness_weight=0.6,
+                                        consistency_weight=0.8, pooling=True),
+        'bayesian_smooth': loss_config('bayesian'),
+    }
+
+
+def run_ours(dev, stereo, preds, cfg, materialise=False):
+    from uncertainty_model_b200.train import loss as L
+    from uncertainty_model_b200.train import utils as U
+    images = stereo.to(dev)
+    gp = [p.to(dev).clone().requires_grad_(True) for p in preds]
+    pyr = U.scale_pyramid(images, len(gp))
+    rec = U.reconstruct_pyramid(gp, pyr)
+    if materialise:
+        rec = list(rec)
+    fn = L.TukraUncertaintyLoss(**cfg).to(dev)
+    dl, el = fn(pyr, gp, rec, 0, None)
+    (dl + el).backward()
+    return dl, el, gp, pyr, rec, fn
+
+
+# ------------------------------------------------------------------ pyramid --
+def test_pyramid_matches_reference(dev):
+    from uncertainty_model_b200.train import utils as U
+    g = load('loss_l1_default.npz')
+    stereo = torch.cat([torch.from_numpy(g['left']),
+                        torch.from_numpy(g['right'])], 1).to(dev)
+    pyr = U.scale_pyramid(stereo, 4)
+    assert pyr[0].data_ptr() == stereo.data_ptr()      # level 0 is aliased
+    for i in range(4):
+        assert pyr[i].shape == g[f'pyr{i}_f32'].shape
+        assert np.allclose(pyr[i].cpu().numpy(), g[f'pyr{i}_f32'], atol=5e-7)
+
+
+def test_pyramid_odd_shapes_and_channel_slices(dev):
+    from oracle import loss_port as P
+    from uncertainty_model_b200.train import utils as U
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(3, 8, 37, 53, generator=g)
+    ours = U.scale_pyramid(x.to(dev)[:, 1:7], 3)       # strided batch
+    ref = P.pyramid(x[:, 1:7], 3)
+    for a, b in zip(ours, ref):
+        assert np.allclose(a.cpu().numpy(), b.numpy(), atol=5e-7)
+
+
+# --------------------------------------------------------------------- warp --
+def test_reconstruct_matches_reference(dev):
+    from uncertainty_model_b200.train import utils as U
+    g = load('components.npz')
+    im = torch.from_numpy(g['images']).to(dev)
+    pr = torch.from_numpy(g['pred']).to(dev)
+    left = U.reconstruct_left_image(pr[:, 0:1], im[:, 3:6])
+    right = U.reconstruct_right_image(pr[:, 1:2], im[:, 0:3])
+    assert np.allclose(left.cpu().numpy(), g['recon_left_f64'], atol=5e-6)
+    assert np.allclose(right.cpu().numpy(), g['recon_right_f64'], atol=5e-6)
+    gen = U.reconstruct(-pr[:, 0:1], im[:, 3:6])
+    assert torch.equal(gen, left)
+
+
+def test_reconstruct_pyramid_is_lazy_and_differentiable(dev):
+    from oracle import loss_port as P
+    from oracle.make_golden import make_inputs
+    from uncertainty_model_b200.train import utils as U
+    left, right, preds = make_inputs(2, 32, 48, 0.5, 7)
+    stereo = torch.cat([left, right], 1)
+    gp = [p.to(dev).requires_grad_(True) for p in preds]
+    pyr = U.scale_pyramid(stereo.to(dev), 4)
+    rec = U.reconstruct_pyramid(gp, pyr)
+    assert not rec.materialised and len(rec) == 4
+    w = [torch.rand_like(r) for r in rec]               # materialises
+    assert rec.materialised
+    sum((r * k).sum() for r, k in zip(rec, w)).backward()
+
+    op = [p.double().requires_grad_(True) for p in preds]
+    orec = P.recon_pyramid(op, P.pyramid(stereo.double(), 4))
+    sum((r * k.cpu().double()).sum() for r, k in zip(orec, w)).backward()
+    for i in range(4):
+        assert np.allclose(rec[i].detach().cpu().numpy(),
+                           orec[i].detach().numpy(), atol=2e-5)
+        assert rel_l2(gp[i].grad.cpu().numpy(), op[i].grad.numpy()) < GRAD_REL
+
+
+# --------------------------------------------------------------- fused loss --
+@pytest.mark.parametrize('name', sorted(cases()))
+@pytest.mark.parametrize('materialise', [False, True])
+def test_total_loss_matches_reference_fixture(dev, name, materialise):
+    cfg = cases()[name]
+    g = load(f'loss_{name}.npz')
+    stereo = torch.cat([torch.from_numpy(g['left']),
+                        torch.from_numpy(g['right'])], 1)
+    preds = [torch.from_numpy(g[f'pred{i}']) for i in range(4)]
+    dl, el, gp, pyr, rec, fn = run_ours(dev, stereo, preds, cfg, materialise)
+    for mine, key in ((dl, 'disp_loss'), (el, 'error_loss')):
+        for tag in ('f32', 'f64'):
+            ref = float(g[f'{key}_{tag}'])
+            assert abs(mine.item() - ref) <= LOSS_REL * abs(ref), \
+                (key, tag, mine.item(), ref)
+    for i in range(4):
+        r = rel_l2(gp[i].grad.cpu().numpy(), g[f'grad{i}_f64'])
+        assert r < GRAD_REL, (i, r)
+    # loss.py:548 -- the last scale's error map stays readable
+    prev = fn.wssim.previous_image_error
+    assert np.allclose(prev.cpu().numpy(), g['err3_f32'], atol=1e-5)
+
+
+@pytest.mark.parametrize('loss_type', ['l1', 'bayesian', 'log_bayesian'])
+@pytest.mark.parametrize('shape', [(2, 64, 128, 0.3), (1, 96, 160, 1.0),
+                                   (3, 40, 600, 0.3)])
+def test_total_loss_matches_oracle(dev, loss_type, shape):
+    """Seeded inputs, CPU oracle in fp64; (3,40,600) spans several column
+    tiles and exercises the seams."""
+    from oracle import loss_port as P
+    from oracle.make_golden import loss_config, make_inputs
+    b, h, w, scale = shape
+    cfg = loss_config(loss_type, smoothness_weight=0.25)
+    left, right, preds = make_inputs(b, h, w, scale, 31)
+    stereo = torch.cat([left, right], 1)
+    rdl, rel, rgrads = P.step(stereo.double(), [p.double() for p in preds], cfg)
+    dl, el, gp, *_ = run_ours(dev, stereo, preds, cfg)
+    assert abs(dl.item() - float(rdl)) <= LOSS_REL * abs(float(rdl))
+    assert abs(el.item() - float(rel)) <= LOSS_REL * abs(float(rel))
+    for i in range(4):
+        assert rel_l2(gp[i].grad.cpu().numpy(), rgrads[i].numpy()) < GRAD_REL
+
+
+def test_separate_upstream_gradients(dev):
+    """disp_loss and error_loss back-propagated with different weights."""
+    from oracle import loss_port as P
+    from oracle.make_golden import loss_config, make_inputs
+    from uncertainty_model_b200.train import loss as L
+    from uncertainty_model_b200.train import utils as U
+    cfg = loss_config('bayesian', smoothness_weight=0.5)
+    left, right, preds = make_inputs(2, 48, 80, 0.4, 17)
+    stereo = torch.cat([left, right], 1)
+    op = [p.double().requires_grad_(True) for p in preds]
+    opyr = P.pyramid(stereo.double(), 4)
+    odl, oel = P.total_loss(opyr, op, P.recon_pyramid(op, opyr), cfg)
+    (0.3 * odl - 2.0 * oel).backward()
+    gp = [p.to(dev).requires_grad_(True) for p in preds]
+    pyr = U.scale_pyramid(stereo.to(dev), 4)
+    dl, el = L.TukraUncertaintyLoss(**cfg)(pyr, gp,
+                                           U.reconstruct_pyramid(gp, pyr))
+    (0.3 * dl - 2.0 * el).backward()
+    for i in range(4):
+        assert rel_l2(gp[i].grad.cpu().numpy(), op[i].grad.numpy()) < GRAD_REL
+    # only one of the two outputs used
+    gp2 = [p.to(dev).requires_grad_(True) for p in preds]
+    dl2, _ = L.TukraUncertaintyLoss(**cfg)(pyr, gp2,
+                                           U.reconstruct_pyramid(gp2, pyr))
+    dl2.backward()
+    op2 = [p.double().requires_grad_(True) for p in preds]
+    odl2, _ = P.total_loss(opyr, op2, P.recon_pyramid(op2, opyr), cfg)
+    odl2.backward()
+    for i in range(4):
+        assert rel_l2(gp2[i].grad.cpu().numpy(), op2[i].grad.numpy()) < GRAD_REL
+
+
+def test_backward_is_bitwise_deterministic(dev):
+    from oracle.make_golden import loss_config, make_inputs
+    cfg = loss_config('bayesian', smoothness_weight=0.5)
+    left, right, preds = make_inputs(4, 64, 256, 1.0, 5)
+    stereo = torch.cat([left, right], 1)
+    runs = []
+    for _ in range(3):
+        dl, el, gp, *_ = run_ours(dev, stereo, preds, cfg)
+        runs.append((dl.item(), el.item(), [p.grad.clone() for p in gp]))
+    for r in runs[1:]:
+        assert r[0] == runs[0][0] and r[1] == runs[0][1]
+        for a, b in zip(r[2], runs[0][2]):
+            assert torch.equal(a, b)
+
+
+def test_anchor_configs_full_size(dev):
+    """Full-size seeded anchors of BASELINE.json configs 1, 2, 3 (one shard)
+    and 4 (reduced batch): reference fp32 scalars stored in anchors.npz."""
+    from oracle.make_golden import loss_config, make_inputs
+    g = load('anchors.npz')
+    for name, lt in (('c1', 'l1'), ('c2', 'bayesian'), ('c3_shard', 'l1'),
+                     ('c4', 'l1')):
+        b, h, w = [int(v) for v in g[f'{name}_shape']]
+        left, right, preds = make_inputs(b, h, w, 0.3, 0)
+        dl, el, gp, *_ = run_ours(dev, torch.cat([left, right], 1), preds,
+                                  loss_config(lt))
+        for mine, key in ((dl, 'disp_loss'), (el, 'error_loss')):
+            ref = float(g[f'{name}_{key}'])
+            assert abs(mine.item() - ref) <= LOSS_REL * abs(ref), (name, key)
+        l2 = np.array([float(p.grad.double().norm()) for p in gp])
+        assert np.allclose(l2, g[f'{name}_grad_l2'], rtol=1e-4), name
+        gs = np.array([float(p.grad.double().sum()) for p in gp])
+        assert np.allclose(gs, g[f'{name}_grad_sum'], rtol=1e-3,
+                           atol=1e-6), name
+
+
+def test_batch_shard_additivity(dev):
+    """loss(B) equals the mean of the shard losses and the
+    raw term sums add up -- the property the multi-GPU path relies on."""
+    from oracle.make_golden import loss_config, make_inputs
+    from uncertainty_model_b200.train import loss as L
+    from uncertainty_model_b200.train import utils as U
+    cfg = loss_config('bayesian')
+    left, right, preds = make_inputs(4, 32, 64, 0.3, 9)
+    stereo = torch.cat([left, right], 1).to(dev)
+    preds = [p.to(dev) for p in preds]
+
+    def run(lo, hi, world):
+        fn = L.TukraUncertaintyLoss(**cfg)
+        fn.world_size = world
+        gp = [p[lo:hi].clone().requires_grad_(True) for p in preds]
+        pyr = U.scale_pyramid(stereo[lo:hi].contiguous(), 4)
+        dl, el = fn(pyr, gp, U.reconstruct_pyramid(gp, pyr))
+        (dl + el).backward()
+        return dl, el, gp, fn.last_term_sums
+
+    dl, el, gp, sums = run(0, 4, 1)
+    a = run(0, 2, 2)
+    b = run(2, 4, 2)
+    assert torch.allclose(a[3] + b[3], sums, rtol=1e-6)
+    assert abs((a[0] + b[0]).item() - dl.item()) < LOSS_REL * abs(dl.item())
+    assert abs((a[1] + b[1]).item() - el.item()) < LOSS_REL * abs(el.item())
+    for i in range(4):
+        cat = torch.cat([a[2][i].grad, b[2][i].grad], 0)
+        assert rel_l2(cat.cpu().numpy(), gp[i].grad.cpu().numpy()) < 1e-5
+
+
+# --------------------------------------------------------------- components --
+def test_component_modules_match_reference_fixture(dev):
+    from uncertainty_model_b200.train import loss as L
+    g = load('components.npz')
+    im = torch.from_numpy(g['images']).to(dev)
+    er = torch.from_numpy(g['error']).to(dev)
+
+    def fresh(key):
+        return torch.from_numpy(g[key]).to(dev).requires_grad_(True)
+
+    def check(val, wrt, key):
+        grad, = torch.autograd.grad(val, wrt)
+        ref = float(g[f'{key}_f64'])
+        assert abs(val.item() - ref) <= LOSS_REL * abs(ref), key
+        assert rel_l2(grad.cpu().numpy(), g[f'{key}_grad_f64']) < GRAD_REL, key
+
+    for alpha in (0.85, 1.0):
+        rc = fresh('recon')
+        ws = L.WeightedSSIMLoss(alpha)
+        e = ws.image_error(im, rc)
+        assert not e.requires_grad
+        assert np.allclose(e.cpu().numpy(), g[f'image_error_a{alpha}_f64'],
+                           atol=1e-5)
+        check(ws(im, rc), rc, f'wssim_a{alpha}')
+        assert torch.equal(ws.previous_image_error, e)
+    pr = fresh('pred')
+    check(L.ConsistencyLoss()(pr[:, 0:2]), pr, 'cons')
+    pr = fresh('pred')
+    check(L.ConsistencyLoss()(pr[:, 2:4], pr[:, 0:2]), pr, 'cons_ab')
+    pr = fresh('pred')
+    check(L.SmoothnessLoss()(pr[:, 0:2], im), pr, 'smooth')
+    for lt in ('l1', 'bayesian', 'log_bayesian'):
+        for pooling in (False, True):
+            pr = fresh('pred')
+            fn = L.ReprojectionErrorLoss(lt, 0.7, 0.3, pooling)
+            check(fn(pr, im, er), pr,
+                  f'reproj_{lt}_{"pool" if pooling else "nopool"}')
+
+
+def test_zero_weight_terms_vanish(dev):
+    from oracle.make_golden import make_inputs
+    from uncertainty_model_b200.train import loss as L
+    from uncertainty_model_b200.train import utils as U
+    left, right, preds = make_inputs(1, 32, 64, 0.3, 2)
+    stereo = torch.cat([left, right], 1).to(dev)
+    gp = [p.to(dev).requires_grad_(True) for p in preds]
+    pyr = U.scale_pyramid(stereo, 4)
+    fn = L.TukraUncertaintyLoss(
+        wssim_weight=0.0, consistency_weight=0.0, smoothness_weight=0.0,
+        predictive_error_weight=0.0,
+        error_loss_config=dict(loss_type='l1', smoothness_weight=0,
+                               consistency_weight=0))
+    dl, el = fn(pyr, gp, U.reconstruct_pyramid(gp, pyr))
+    (dl + el).backward()
+    assert dl.item() == 0.0 and el.item() == 0.0
+    assert all(float(p.grad.abs().max()) == 0.0 for p in gp)
+
+
+def test_adversarial_path_with_a_discriminator(dev):
+    """loss.py:552-558: generator + perceptual terms consume the materialised
+    reconstructions; gradients flow through them into the predictions."""
+    from oracle import loss_port as P
+    from oracle.make_golden import loss_config, make_inputs
+    from uncertainty_model_b200.train import loss as L
+    from uncertainty_model_b200.train import utils as U
+
+    class TinyDisc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.conv = torch.nn.ModuleList(
+                [torch.nn.Conv2d(6, 4, 3, padding=1) for _ in range(4)])
+
+        def features(self, pyramid):
+            return [torch.tanh(c(x)) for c, x in zip(self.conv, pyramid)]
+
+        def forward(self, pyramid):
+            f = self.features(pyramid)
+            return torch.sigmoid(sum(x.mean(dim=(1, 2, 3)) for x in f))[:, None]
+
+    cfg = loss_config('l1')
+    left, right, preds = make_inputs(2, 32, 64, 0.3, 8)
+    stereo = torch.cat([left, right], 1)
+    disc = TinyDisc()
+
+    op = [p.clone().requires_grad_(True) for p in preds]
+    opyr = P.pyramid(stereo, 4)
+    orec = P.recon_pyramid(op, opyr)
+    odl, oel = P.total_loss(opyr, op, orec, cfg)
+    verdict = disc(orec)
+    odl = odl + 0.85 * torch.nn.functional.mse_loss(
+        verdict, torch.ones_like(verdict))
+    odl = odl + 0.05 * sum((a - b).abs().mean() for a, b in
+                           zip(disc.features(opyr), disc.features(orec)))
+    (odl + oel).backward()
+
+    gdisc = TinyDisc().to(dev)
+    gp = [p.to(dev).requires_grad_(True) for p in preds]
+    pyr = U.scale_pyramid(stereo.to(dev), 4)
+    rec = U.reconstruct_pyramid(gp, pyr)
+    dl, el = L.TukraUncertaintyLoss(**cfg)(pyr, gp, rec, 7, gdisc)
+    (dl + el).backward()
+    assert abs(dl.item() - odl.item()) < 2e-5 * abs(odl.item())
+    assert abs(el.item() - oel.item()) < 2e-5 * abs(oel.item())
+    for i in range(4):
+        assert rel_l2(gp[i].grad.cpu().numpy(), op[i].grad.numpy()) < 5e-4
+
+
+def test_errors(dev):
+    from uncertainty_model_b200.train import loss as L
+    from uncertainty_model_b200.train import utils as U
+    with pytest.raises(ValueError, match='Loss must be either'):
+        L.TukraUncertaintyLoss(error_loss_config=dict(loss_type='huber'))
+    with pytest.raises(ValueError, match='no CPU fallback'):
+        U.scale_pyramid(torch.rand(1, 6, 16, 16), 2)
+    with pytest.raises(TypeError):
+        U.scale_pyramid(torch.rand(1, 6, 16, 16, dtype=torch.float64,
+                                   device=dev), 2)

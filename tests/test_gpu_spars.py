@@ -1,0 +1,115 @@
+"""GPU parity tests of the sparsification / AUSE path: pooled keys, the sort
+permutation, the curves and the AUSE are bit-exact against the canonical CPU
+oracle (oracle/spars_port.py) and match the reference's own fp32 outputs
+(tests/golden/spars.npz) to 1e-6."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    from uncertainty_model_b200 import _lib
+    _lib.lib()
+    return torch.device('cuda:0')
+
+
+@pytest.mark.parametrize('name', ['small', 'ties', 'ragged'])
+def test_fixture_cases_bit_exact(dev, name):
+    from oracle import spars_port as SP
+    from uncertainty_model_b200.train import sparsification as S
+    g = np.load(os.path.join(GOLDEN, 'spars.npz'))
+    err_np, unc_np = g[f'{name}_err'], g[f'{name}_unc']
+    err = torch.from_numpy(err_np).to(dev)
+    unc = torch.from_numpy(unc_np).to(dev)
+
+    acc, rows, parts = S.curve_sums(err, unc, return_order=True)
+    f = err.shape[0]
+    # pooled maps == ATen avg_pool2d bit for bit
+    assert np.array_equal(parts['pooled_oracle'].cpu().numpy().reshape(f, 2, -1),
+                          g[f'{name}_pooled_err'].reshape(f, 2, -1))
+    assert np.array_equal(parts['pooled_pred'].cpu().numpy().reshape(f, 2, -1),
+                          g[f'{name}_pooled_unc'].reshape(f, 2, -1))
+    # permutation == torch argsort(descending=True, stable=True)
+    assert np.array_equal(parts['order'].cpu().numpy().reshape(f, 2, -1),
+                          g[f'{name}_stable_order_unc'])
+
+    oc = S.curve(err, err, device=dev)
+    pc = S.curve(err, unc, device=dev)
+    ref_oc, oparts = SP.curve_canonical(err_np, err_np, return_parts=True)
+    ref_pc, pparts = SP.curve_canonical(err_np, unc_np, return_parts=True)
+    assert np.array_equal(acc.cpu().numpy(), pparts['row_norm_sum'])
+    assert np.array_equal(oc.cpu().numpy(), ref_oc)
+    assert np.array_equal(pc.cpu().numpy(), ref_pc)
+    a = S.ause(oc, pc)
+    assert np.float32(a.item()) == SP.ause_canonical(ref_oc, ref_pc)
+    assert np.float32(S.ause(oc.cpu(), pc.cpu()).item()) == np.float32(a.item())
+    assert np.float32(S.aurg(pc, oc).item()) == \
+        SP.ause_canonical(ref_pc, ref_oc)
+    # against the reference's own fp32 results
+    assert np.allclose(oc.cpu().numpy(), g[f'{name}_oracle_curve'], rtol=2e-6)
+    if name != 'ties':     # the reference's argsort is unstable on ties
+        assert np.allclose(pc.cpu().numpy(), g[f'{name}_pred_curve'],
+                           rtol=2e-6)
+        assert abs(a.item() - float(g[f'{name}_ause'])) < 1e-6
+
+
+def test_c5_shape_against_reference_anchor(dev):
+    """4 frames of the SCARED-shape 1024x1280 case."""
+    from oracle import spars_port as SP
+    from uncertainty_model_b200.train import sparsification as S
+    g = np.load(os.path.join(GOLDEN, 'spars.npz'))
+    err, unc = SP.synthetic_maps(4, 1024, 1280, seed=0)
+    err, unc = err.to(dev), unc.to(dev)
+    oc = S.curve(err, err, device=dev)
+    pc = S.curve(err, unc, device=dev)
+    assert np.allclose(oc.cpu().numpy(), g['c5_4frames_oracle_curve'],
+                       rtol=2e-6)
+    assert np.allclose(pc.cpu().numpy(), g['c5_4frames_pred_curve'], rtol=2e-6)
+    assert abs(S.ause(oc, pc).item() - float(g['c5_4frames_ause'])) < 1e-7
+    # size-independent properties at full size
+    acc, rows, parts = S.curve_sums(err[:1], unc[:1], return_order=True)
+    order = parts['order'].long()
+    keys = parts['pooled_pred']
+    sorted_keys = torch.gather(keys, 1, order)
+    assert bool((sorted_keys[:, 1:] <= sorted_keys[:, :-1]).all())   # sorted
+    tie = sorted_keys[:, 1:] == sorted_keys[:, :-1]
+    assert bool((order[:, 1:][tie] > order[:, :-1][tie]).all())      # stable
+    assert bool((torch.sort(order, dim=1).values ==
+                 torch.arange(order.shape[1], device=dev)).all())    # perm
+    assert oc[0].item() == 1.0 and pc[0].item() == 1.0
+    # the oracle ranking is the best possible one
+    assert bool((oc <= pc + 1e-6).all())
+
+
+def test_chunked_processing_is_identical(dev, monkeypatch):
+    from oracle import spars_port as SP
+    from uncertainty_model_b200.train import sparsification as S
+    err, unc = SP.synthetic_maps(5, 40, 56, seed=4)
+    err, unc = err.to(dev), unc.to(dev)
+    full = S.curve(err, unc, device=dev)
+    monkeypatch.setattr(S, 'WORKSPACE_BUDGET_BYTES', 1)   # one row at a time
+    chunked = S.curve(err, unc, device=dev)
+    assert torch.equal(full, chunked)
+
+
+def test_random_curve_and_errors(dev):
+    from uncertainty_model_b200.train import sparsification as S
+    err = torch.rand(1, 2, 30, 40, device=dev)
+    rc = S.random_curve(err, device=dev)
+    assert rc.shape == (100,) and rc.dtype == torch.float32
+    assert rc[0].item() == 1.0
+    assert S.curve(err, err).device.type == 'cpu'      # reference default
+    with pytest.raises(Exception, match='different step sizes'):
+        S.ause(torch.zeros(3), torch.zeros(4))
+    with pytest.raises(ValueError):
+        S.curve(err.cpu(), err.cpu())
+    with pytest.raises(ValueError):
+        S.curve(err[:, :, :8, :8], err[:, :, :8, :8])

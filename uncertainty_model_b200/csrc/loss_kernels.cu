@@ -1,0 +1,383 @@
+// Kernels (1) and (2): fused multi-scale loss forward / backward launches.
+// The per-phase arithmetic lives in loss_core.cuh / cons_core.cuh (shared with
+// the CPU emulation harness in tests/emu); this file owns the CTA scheduling,
+// the shared-memory arenas, the warp-serial scatter and the reductions.
+//
+// All pyramid scales of a step go out in ONE launch: blockIdx.x indexes the
+// concatenation of the per-scale tile lists (largest scale first, so the long
+// CTAs start first and the small scales fill the tail of the wave).
+#include <stdlib.h>
+
+#include "cons_core.cuh"
+#include "usl_common.cuh"
+
+namespace usl {
+
+struct MultiParams {
+    LossParams P[USL_MAX_SCALES];
+    int cta_start[USL_MAX_SCALES + 1];
+    int tiles_x[USL_MAX_SCALES], strips[USL_MAX_SCALES];
+    int n;
+};
+
+struct MultiCons {
+    ConsParams P[USL_MAX_SCALES];
+    int cta_start[USL_MAX_SCALES + 1];
+    int strips[USL_MAX_SCALES];
+    int n;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(640)
+loss_main_kernel(const __grid_constant__ MultiParams M) {
+    extern __shared__ float4 smem_raw[];
+    __shared__ float red[20][NUM_ACC];
+
+    int s = 0;
+    while (s + 1 < M.n && (int)blockIdx.x >= M.cta_start[s + 1]) ++s;
+    const LossParams& P = M.P[s];
+    int local = blockIdx.x - M.cta_start[s];
+    Tile T;
+    const int tx = local % M.tiles_x[s]; local /= M.tiles_x[s];
+    const int st = local % M.strips[s];
+    T.b = local / M.strips[s];
+    T.xa = tx * P.TW; T.xb = min(P.w, T.xa + P.TW);
+    T.ya = st * P.R; T.yb = min(P.h, T.ya + P.R);
+    T.cbeg = T.xa - HALO_L;
+    T.cta = blockIdx.x;
+
+    const Rings S = carve(P, reinterpret_cast<float*>(smem_raw), BWD);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int LWp = (P.LW + 31) & ~31;
+    float acc[NUM_ACC];
+#pragma unroll
+    for (int k = 0; k < NUM_ACC; ++k) acc[k] = 0.0f;
+    float gd_up = 0.0f, ge_up = 0.0f;
+    if (BWD) {
+        gd_up = P.gout_d ? __ldg(P.gout_d) : 0.0f;
+        ge_up = P.gout_e ? __ldg(P.gout_e) : 0.0f;
+        phase_init_bwd(P, T, S, tid, nt);
+    }
+    const int r1 = last_step(T);
+    for (int r = first_step(T); r <= r1; ++r) {
+        phase_A(P, T, S, r, tid, nt);
+        __syncthreads();
+        phase_B<BWD>(P, T, S, r, tid, nt, LWp, acc, gd_up, ge_up);
+        __syncthreads();
+        phase_C<BWD>(P, T, S, r, tid, nt, LWp, gd_up);
+        __syncthreads();
+        phase_D<BWD>(P, T, S, r, tid, nt, LWp, acc, gd_up, ge_up);
+    }
+    if (!BWD) {
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int k = 0; k < NUM_ACC; ++k) {
+            const float v = warp_sum(acc[k]);
+            if (lane == 0) red[warp][k] = v;
+        }
+        __syncthreads();
+        if (tid < NUM_ACC) {
+            float t = 0.0f;
+            const int nw = (nt + 31) >> 5;
+            for (int i = 0; i < nw; ++i) t += red[i][tid];
+            P.partials[(long long)(blockIdx.x - M.cta_start[s]) * NUM_ACC + tid] = t;
+        }
+    }
+}
+
+// One warp scatters the sources of one row (one view, both terms) into the
+// destination row `Hrow`.  Chunks of 32 columns in order; duplicates inside a
+// chunk are folded by the lowest lane of each group in lane order.
+__device__ __forceinline__ void scatter_row_warp(float* Hrow, const int* dest,
+                                                 const float* c0,
+                                                 const float* c1, int w,
+                                                 int lane) {
+    for (int base = 0; base < w; base += 32) {
+        const int x = base + lane;
+        const bool valid = x < w;
+        const int d = valid ? dest[x] : (-1000000 - lane);
+        const float a0 = valid ? c0[x] : 0.0f;
+        const float a1 = valid ? c1[x] : 0.0f;
+        unsigned grp = __match_any_sync(0xffffffffu, d);
+        const bool leader = (__ffs(grp) - 1) == lane;
+        float s0 = 0.0f, s1 = 0.0f;
+        while (__any_sync(0xffffffffu, grp != 0u)) {
+            const int src = grp ? (__ffs(grp) - 1) : lane;
+            const float v0 = __shfl_sync(0xffffffffu, a0, src);
+            const float v1 = __shfl_sync(0xffffffffu, a1, src);
+            if (grp) { s0 += v0; s1 += v1; grp &= grp - 1; }
+        }
+        if (leader && valid && d >= 0 && d < w) Hrow[d] += s0;
+        __syncwarp();
+        if (leader && valid && d + 1 >= 0 && d + 1 < w) Hrow[d + 1] += s1;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cons_scatter_kernel(const __grid_constant__ MultiCons M) {
+    extern __shared__ float4 smem_raw[];
+    int s = 0;
+    while (s + 1 < M.n && (int)blockIdx.x >= M.cta_start[s + 1]) ++s;
+    const ConsParams& P = M.P[s];
+    const int local = blockIdx.x - M.cta_start[s];
+    ConsTile T;
+    T.b = local / M.strips[s];
+    T.ya = (local % M.strips[s]) * P.R;
+    T.yb = min(P.h, T.ya + P.R);
+    const ConsRings S = cons_carve(P.w, reinterpret_cast<float*>(smem_raw));
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const float gd_up = P.gout_d ? __ldg(P.gout_d) : 0.0f;
+    const float ge_up = P.gout_e ? __ldg(P.gout_e) : 0.0f;
+    const int r1 = cons_last_step(T);
+    for (int r = cons_first_step(T); r <= r1; ++r) {
+        cons_phase_A(P, T, S, r, tid, nt);
+        __syncthreads();
+        cons_phase_B(P, T, S, r, tid, nt, gd_up, ge_up);
+        __syncthreads();
+        if (warp < 2 && r >= 0 && r < P.h) {
+            const int v = warp;      // source view; destination is the other
+            float* Hrow = S.H + ((size_t)mod4(r) * 2 + (1 - v)) * P.w;
+            for (int term = 0; term < 2; ++term) {
+                if (!(P.terms & (term ? TERM_CONS_U : TERM_CONS_D))) continue;
+                const size_t j = (size_t)(term * 2 + v) * P.w;
+                scatter_row_warp(Hrow, S.dest + j, S.c0 + j, S.c1 + j, P.w, lane);
+            }
+        }
+        __syncthreads();
+        cons_phase_D(P, T, S, r, tid, nt);
+    }
+}
+
+struct CtaStarts { int v[USL_MAX_SCALES + 1]; };
+
+__global__ void reduce_partials_kernel(const float* partials,
+                                       const CtaStarts starts_, int n_scales,
+                                       double* sums) {
+    const int* starts = starts_.v;
+    // one thread per (scale, term): fixed-order fp64 sum over that scale's CTAs
+    const int i = threadIdx.x;
+    if (i >= n_scales * NUM_ACC) return;
+    const int s = i / NUM_ACC, k = i % NUM_ACC;
+    double t = 0.0;
+    for (int c = starts[s]; c < starts[s + 1]; ++c)
+        t += (double)partials[(long long)c * NUM_ACC + k];
+    sums[i] = t;
+}
+
+__global__ void combine_kernel(const double* sums, const float* coef,
+                               int n_scales, float* out_d, float* out_e) {
+    if (threadIdx.x >= 2) return;
+    const int o = threadIdx.x;
+    double t = 0.0;
+    for (int s = 0; s < n_scales; ++s)
+        for (int k = 0; k < 3; ++k) {
+            const int i = s * NUM_ACC + o * 3 + k;
+            t += (double)coef[i] * sums[i];
+        }
+    if (o == 0) *out_d = (float)t; else *out_e = (float)t;
+}
+
+// ------------------------------------------------------------------ host ---
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const int x = atoi(v);
+    return x > 0 ? x : dflt;
+}
+
+static void choose_tiling(int h, int w, bool bwd, int* TW, int* R) {
+    int tw = env_int(bwd ? "USL_BWD_TW" : "USL_FWD_TW", bwd ? 128 : 256);
+    int r = env_int(bwd ? "USL_BWD_R" : "USL_FWD_R", 32);
+    if (tw > w) tw = w;
+    // even out the column tiles
+    const int nx = (w + tw - 1) / tw;
+    tw = (w + nx - 1) / nx;
+    if (r > h) r = h;
+    const int ny = (h + r - 1) / r;
+    r = (h + ny - 1) / ny;
+    *TW = tw; *R = r;
+}
+
+static int fill_params(const UslLossConfig* cfg, const UslLossScale* s,
+                       bool bwd, LossParams* P) {
+    if (!cfg || !s || s->B <= 0) return USL_ERR_ARG;
+    if (s->h < 3 || s->w < 3) return USL_ERR_UNSUPPORTED;
+    if (cfg->loss_type < 0 || cfg->loss_type > 2) return USL_ERR_ARG;
+    const unsigned t = cfg->terms;
+    if ((t & (TERM_REPROJ | TERM_SMOOTH_D | TERM_SMOOTH_U)) && !s->images &&
+        !(s->err_in && !(t & (TERM_SMOOTH_D | TERM_SMOOTH_U))))
+        return USL_ERR_ARG;
+    const bool need_disp = (t & (TERM_CONS_D | TERM_CONS_U | TERM_SMOOTH_D)) ||
+                           ((t & TERM_REPROJ) && !s->recon_in && !s->err_in);
+    if (need_disp && !s->disp) return USL_ERR_ARG;
+    if ((t & (TERM_UNC | TERM_SMOOTH_U | TERM_CONS_U)) && !s->unc)
+        return USL_ERR_ARG;
+    if ((t & TERM_UNC) && !(t & TERM_REPROJ) && !s->err_in) return USL_ERR_ARG;
+    LossParams p = {};
+    p.B = s->B; p.h = s->h; p.w = s->w;
+    p.img = s->images; p.img_bs = s->img_bs; p.img_cs = s->img_cs;
+    p.disp = s->disp; p.d_bs = s->disp_bs; p.d_cs = s->disp_cs;
+    p.unc = s->unc; p.u_bs = s->unc_bs; p.u_cs = s->unc_cs;
+    p.recon_in = s->recon_in; p.ri_bs = s->rin_bs; p.ri_cs = s->rin_cs;
+    p.err_in = s->err_in; p.ei_bs = s->ein_bs; p.ei_cs = s->ein_cs;
+    p.recon_out = s->recon_out; p.err_out = s->err_out;
+    p.grad_recon_in = s->grad_recon_in;
+    p.grad_disp = s->grad_disp; p.gd_bs = s->gd_bs; p.gd_cs = s->gd_cs;
+    p.grad_unc = s->grad_unc; p.gu_bs = s->gu_bs; p.gu_cs = s->gu_cs;
+    p.grad_recon_out = s->grad_recon_out;
+    p.terms = t; p.loss_type = cfg->loss_type;
+    p.recon_given = s->recon_in != nullptr;
+    p.err_given = s->err_in != nullptr;
+    p.alpha = cfg->alpha; p.c1 = cfg->c1; p.c2 = cfg->c2;
+    for (int k = 0; k < NUM_ACC; ++k) p.coef[k] = cfg->coef[k];
+    if (bwd && p.recon_given && (t & TERM_REPROJ) && !p.err_given &&
+        !p.grad_recon_out)
+        return USL_ERR_ARG;
+    if (p.recon_out && (p.recon_given || !(t & TERM_REPROJ))) return USL_ERR_ARG;
+    choose_tiling(p.h, p.w, bwd, &p.TW, &p.R);
+    p.LW = p.TW + HALO_L + HALO_R;
+    *P = p;
+    return USL_OK;
+}
+
+static int plan(const UslLossConfig* cfgs, const UslLossScale* scales, int n,
+                bool bwd, MultiParams* M, size_t* smem, int* threads) {
+    if (n < 1 || n > USL_MAX_SCALES) return USL_ERR_ARG;
+    M->n = n;
+    M->cta_start[0] = 0;
+    *smem = 0;
+    int maxLWp = 32;
+    for (int i = 0; i < n; ++i) {
+        const int rc = fill_params(&cfgs[i], &scales[i], bwd, &M->P[i]);
+        if (rc != USL_OK) return rc;
+        const LossParams& p = M->P[i];
+        M->tiles_x[i] = (p.w + p.TW - 1) / p.TW;
+        M->strips[i] = (p.h + p.R - 1) / p.R;
+        M->cta_start[i + 1] =
+            M->cta_start[i] + M->tiles_x[i] * M->strips[i] * p.B;
+        const size_t bytes = ring_floats(p, bwd) * sizeof(float);
+        if (bytes > *smem) *smem = bytes;
+        const int LWp = (p.LW + 31) & ~31;
+        if (LWp > maxLWp) maxLWp = LWp;
+    }
+    if (*smem > 227 * 1024) return USL_ERR_UNSUPPORTED;
+    int nt = 2 * maxLWp;
+    if (nt > 640) nt = maxLWp;       // two passes per step over the item list
+    if (nt > 640) nt = 640;
+    *threads = nt;
+    return USL_OK;
+}
+
+}  // namespace usl
+
+using namespace usl;
+
+extern "C" int usl_loss_fwd_ctas(const UslLossScale* s) {
+    if (!s || s->B <= 0 || s->h < 3 || s->w < 3) return USL_ERR_ARG;
+    int TW, R;
+    choose_tiling(s->h, s->w, false, &TW, &R);
+    return ((s->w + TW - 1) / TW) * ((s->h + R - 1) / R) * s->B;
+}
+
+extern "C" int usl_loss_fwd(const UslLossConfig* cfgs,
+                            const UslLossScale* scales, int n_scales,
+                            float* partials, void* stream) {
+    if (!partials) return USL_ERR_ARG;
+    MultiParams M;
+    size_t smem; int nt;
+    const int rc = plan(cfgs, scales, n_scales, false, &M, &smem, &nt);
+    if (rc != USL_OK) return rc;
+    for (int i = 0; i < n_scales; ++i)
+        M.P[i].partials = partials + (long long)M.cta_start[i] * NUM_ACC;
+    if (cudaFuncSetAttribute(loss_main_kernel<false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return USL_ERR_CUDA;
+    loss_main_kernel<false><<<M.cta_start[n_scales], nt, smem,
+                              (cudaStream_t)stream>>>(M);
+    return check_launch();
+}
+
+extern "C" int usl_loss_reduce(const float* partials, const int* cta_starts,
+                               int n_scales, double* sums, void* stream) {
+    if (!partials || !cta_starts || !sums || n_scales < 1 ||
+        n_scales > USL_MAX_SCALES)
+        return USL_ERR_ARG;
+    CtaStarts st;
+    for (int i = 0; i <= n_scales; ++i) st.v[i] = cta_starts[i];
+    reduce_partials_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(
+        partials, st, n_scales, sums);
+    return check_launch();
+}
+
+extern "C" int usl_loss_combine(const double* sums, const float* coef,
+                                int n_scales, float* out_disp, float* out_err,
+                                void* stream) {
+    if (!sums || !coef || !out_disp || !out_err || n_scales < 1)
+        return USL_ERR_ARG;
+    combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, coef, n_scales,
+                                                       out_disp, out_err);
+    return check_launch();
+}
+
+extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
+                            const UslLossScale* scales, int n_scales,
+                            const float* gout_disp, const float* gout_err,
+                            int stages, void* stream) {
+    if (!(stages & (USL_BWD_STAGE_SCATTER | USL_BWD_STAGE_MAIN)))
+        return USL_ERR_ARG;
+    MultiParams M;
+    size_t smem; int nt;
+    int rc = plan(cfgs, scales, n_scales, true, &M, &smem, &nt);
+    if (rc != USL_OK) return rc;
+    // 1) transposed warp of the consistency terms -> grad_disp (pure store)
+    MultiCons C;
+    C.n = 0; C.cta_start[0] = 0;
+    size_t csmem = 0;
+    for (int i = 0; i < n_scales; ++i) {
+        LossParams& p = M.P[i];
+        p.gout_d = gout_disp; p.gout_e = gout_err;
+        p.grad_disp_accumulate = 0;
+        if (!(p.terms & (TERM_CONS_D | TERM_CONS_U))) continue;
+        if (!p.grad_disp) return USL_ERR_ARG;
+        ConsParams c = {};
+        c.B = p.B; c.h = p.h; c.w = p.w;
+        c.disp = p.disp; c.d_bs = p.d_bs; c.d_cs = p.d_cs;
+        c.unc = p.unc; c.u_bs = p.u_bs; c.u_cs = p.u_cs;
+        c.gout_d = gout_disp; c.gout_e = gout_err;
+        c.grad_disp = p.grad_disp; c.gd_bs = p.gd_bs; c.gd_cs = p.gd_cs;
+        c.terms = p.terms & (TERM_CONS_D | TERM_CONS_U);
+        c.coef_dd = p.coef[ACC_CONS_D]; c.coef_ud = p.coef[ACC_CONS_U];
+        c.R = env_int("USL_CONS_R", 16);
+        if (c.R > c.h) c.R = c.h;
+        const int k = C.n++;
+        C.P[k] = c;
+        C.strips[k] = (c.h + c.R - 1) / c.R;
+        C.cta_start[k + 1] = C.cta_start[k] + C.strips[k] * c.B;
+        const size_t bytes = cons_ring_floats(c.w) * sizeof(float);
+        if (bytes > csmem) csmem = bytes;
+        p.grad_disp_accumulate = 1;
+    }
+    if (C.n > 0 && (stages & USL_BWD_STAGE_SCATTER)) {
+        if (csmem > 227 * 1024) return USL_ERR_UNSUPPORTED;
+        if (cudaFuncSetAttribute(cons_scatter_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)csmem) != cudaSuccess)
+            return USL_ERR_CUDA;
+        cons_scatter_kernel<<<C.cta_start[C.n], 256, csmem,
+                              (cudaStream_t)stream>>>(C);
+        rc = check_launch();
+        if (rc != USL_OK) return rc;
+    }
+    // 2) everything else, adding to the scattered part
+    if (!(stages & USL_BWD_STAGE_MAIN)) return USL_OK;
+    if (cudaFuncSetAttribute(loss_main_kernel<true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return USL_ERR_CUDA;
+    loss_main_kernel<true><<<M.cta_start[n_scales], nt, smem,
+                             (cudaStream_t)stream>>>(M);
+    return check_launch();
+}

@@ -1,0 +1,405 @@
+// Kernel family (4): sparsification curves / AUSE
+// (reference: train/sparsification.py:8-61).
+//
+//   curve(oracle, predicted): avg-pool k x k both maps, sort every row of the
+//   pooled predicted error in descending order, gather the pooled oracle error
+//   in that order, and report for 100 cut points the mean of the remaining
+//   tail, normalised by the row mean and averaged over rows.
+//
+// Pipeline per call (rows = frames * 2 views, n = (H-k+1)*(W-k+1) per row):
+//   pool      bit-exact restatement of ATen avg_pool2d: fp32 window sum in
+//             row-major order, one true division by k*k.  The predicted map is
+//             emitted as a 32-bit radix key whose ascending order is the
+//             descending float order (-0.0 canonicalised to +0.0).
+//   sort      segmented LSD radix sort, 4 passes of 8 bits, stable: equal keys
+//             keep ascending index order, i.e. exactly
+//             argsort(descending=True, stable=True).  Per pass: per-tile digit
+//             histogram -> per-row exclusive scan -> ranked scatter.  Ranking
+//             inside a tile is warp match.any based (atomic-free, order
+//             preserving).  Payload: the pooled oracle value (and, on request,
+//             the element index, which is the argsort itself).
+//   tail      canonical fp64 segment sums between consecutive cut points
+//             (256 lanes, lane-strided, stride-halving tree), suffix scan,
+//             per-row normalisation, fixed-order accumulation over rows.
+// The summation orders are the ones spelled out in oracle/spars_port.py, so
+// keys, permutation, curve and AUSE are compared bit for bit.
+//
+// HBM-bound: algorithmic bytes are 16 B per pooled element (read two maps,
+// write two orderings); the radix passes really move ~20 B/element/pass.
+#include "usl_common.cuh"
+
+namespace usl {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 4096
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int WARP_SPAN = SORT_TILE / SORT_WARPS;      // 512
+constexpr int RADIX = 256;
+constexpr int SEG_LANES = 256;
+
+__device__ __forceinline__ unsigned desc_key(float v) {
+    v = __fadd_rn(v, 0.0f);                     // -0.0 -> +0.0
+    unsigned u = __float_as_uint(v);
+    u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;  // ascending float order
+    return ~u;                                   // ... reversed
+}
+
+// ---- pool ---------------------------------------------------------------
+// Each thread produces PX horizontally adjacent outputs so a window row is
+// loaded once and feeds PX accumulators; every accumulator still adds its
+// k*k values one by one in row-major order.
+constexpr int PX = 4;
+constexpr int KMAX = 15;
+
+__global__ void __launch_bounds__(256)
+pool_kernel(const float* __restrict__ in, int rows, int H, int W, int k,
+            float* __restrict__ out_val, unsigned* __restrict__ out_key) {
+    const int oh = H - k + 1, ow = W - k + 1;
+    const int gx = (ow + PX - 1) / PX;
+    const long long total = (long long)rows * oh * gx;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float div = (float)(k * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+         i < total; i += stride) {
+        const int xg = (int)(i % gx);
+        const int oy = (int)((i / gx) % oh);
+        const int row = (int)(i / ((long long)gx * oh));
+        const int ox = xg * PX;
+        const float* p = in + ((long long)row * H + oy) * W + ox;
+        float acc[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) acc[j] = 0.0f;
+        for (int dy = 0; dy < k; ++dy) {
+            float v[KMAX + PX - 1];
+#pragma unroll
+            for (int j = 0; j < KMAX + PX - 1; ++j)
+                v[j] = (j < k + PX - 1 && ox + j < W) ? __ldg(p + j) : 0.0f;
+#pragma unroll
+            for (int dx = 0; dx < KMAX; ++dx)
+                if (dx < k) {
+#pragma unroll
+                    for (int j = 0; j < PX; ++j)
+                        acc[j] = __fadd_rn(acc[j], v[dx + j]);
+                }
+            p += W;
+        }
+        const long long o = ((long long)row * oh + oy) * ow + ox;
+#pragma unroll
+        for (int j = 0; j < PX; ++j)
+            if (ox + j < ow) {
+                const float m = __fdiv_rn(acc[j], div);
+                if (out_val) out_val[o + j] = m;
+                if (out_key) out_key[o + j] = desc_key(m);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+iota_kernel(int* idx, long long rows, int n) {
+    const long long total = rows * n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+         i < total; i += stride)
+        idx[i] = (int)(i % n);
+}
+
+// ---- sort ---------------------------------------------------------------
+// counts[row][digit][tile]
+__global__ void __launch_bounds__(SORT_THREADS)
+hist_kernel(const unsigned* __restrict__ keys, int n, int ntiles, int shift,
+            unsigned* __restrict__ counts) {
+    __shared__ unsigned h[RADIX];
+    const int row = blockIdx.y, tile = blockIdx.x;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned* k = keys + (long long)row * n;
+    const int base = tile * SORT_TILE;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const int i = base + j * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(k[i] >> shift) & 255u], 1u);   // integer: exact
+    }
+    __syncthreads();
+    counts[((long long)row * RADIX + threadIdx.x) * ntiles + tile] = h[threadIdx.x];
+}
+
+// exclusive scan of the (digit-major, tile-minor) counts of one row
+__global__ void __launch_bounds__(1024)
+scan_kernel(unsigned* __restrict__ counts, int m) {
+    __shared__ unsigned part[1024];
+    unsigned* c = counts + (long long)blockIdx.x * m;
+    const int per = (m + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(m, lo + per);
+    unsigned s = 0;
+    for (int i = lo; i < hi; ++i) s += c[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {      // Hillis-Steele, inclusive
+        unsigned v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = part[threadIdx.x] - s;           // exclusive base
+    for (int i = lo; i < hi; ++i) {
+        const unsigned v = c[i];
+        c[i] = run;
+        run += v;
+    }
+}
+
+template <bool WITH_IDX>
+__global__ void __launch_bounds__(SORT_THREADS)
+scatter_kernel(const unsigned* __restrict__ keys_in,
+               const float* __restrict__ vals_in, const int* __restrict__ idx_in,
+               unsigned* __restrict__ keys_out, float* __restrict__ vals_out,
+               int* __restrict__ idx_out, const unsigned* __restrict__ offsets,
+               int n, int ntiles, int shift) {
+    __shared__ unsigned whist[SORT_WARPS][RADIX];
+    const int row = blockIdx.y, tile = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS)
+        (&whist[0][0])[i] = 0;
+    __syncthreads();
+    const long long rbase = (long long)row * n;
+    const int wbase = tile * SORT_TILE + warp * WARP_SPAN;
+    unsigned key[SORT_ITEMS];
+    unsigned short rank[SORT_ITEMS];
+#pragma unroll
+    for (int c = 0; c < SORT_ITEMS; ++c) {
+        const int i = wbase + c * 32 + lane;
+        const bool valid = i < n;
+        key[c] = valid ? keys_in[rbase + i] : 0u;
+        const unsigned d = (key[c] >> shift) & 255u;
+        const unsigned grp = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
+        const unsigned prev = whist[warp][d];
+        __syncwarp();
+        if (valid && (__ffs(grp) - 1) == lane) whist[warp][d] = prev + __popc(grp);
+        __syncwarp();
+        rank[c] = (unsigned short)(prev + __popc(grp & lt));
+    }
+    __syncthreads();
+    {   // digit threadIdx.x: exclusive bases over the warps of this tile
+        const int d = threadIdx.x;
+        unsigned base = offsets[((long long)row * RADIX + d) * ntiles + tile];
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const unsigned t = whist[w][d];
+            whist[w][d] = base;
+            base += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < SORT_ITEMS; ++c) {
+        const int i = wbase + c * 32 + lane;
+        if (i < n) {
+            const unsigned d = (key[c] >> shift) & 255u;
+            const long long pos = rbase + whist[warp][d] + rank[c];
+            keys_out[pos] = key[c];
+            vals_out[pos] = vals_in[rbase + i];
+            if (WITH_IDX) idx_out[pos] = idx_in[rbase + i];
+        }
+    }
+}
+
+// ---- tail ---------------------------------------------------------------
+struct Cuts { int v[USL_MAX_STEPS + 1]; };
+
+// canonical fp64 sum of sorted values with rank in [cut_k, cut_{k+1})
+__global__ void __launch_bounds__(SEG_LANES)
+segment_kernel(const float* __restrict__ vals, int n, const Cuts cuts,
+               int steps, double* __restrict__ seg) {
+    __shared__ double lanes[SEG_LANES];
+    const int k = blockIdx.x, row = blockIdx.y;
+    const float* v = vals + (long long)row * n;
+    double a = 0.0;
+    for (int i = cuts.v[k] + threadIdx.x; i < cuts.v[k + 1]; i += SEG_LANES)
+        a = __dadd_rn(a, (double)v[i]);
+    lanes[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = SEG_LANES / 2; s >= 1; s >>= 1) {
+        if (threadIdx.x < s)
+            lanes[threadIdx.x] = __dadd_rn(lanes[threadIdx.x], lanes[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seg[(long long)row * steps + k] = lanes[0];
+}
+
+// seg[row][*] -> normalised tail means, in place
+__global__ void row_norm_kernel(double* seg, int rows, int n, const Cuts cuts,
+                                int steps) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    double* s = seg + (long long)row * steps;
+    double run = 0.0;
+    for (int k = steps - 1; k >= 0; --k) {
+        run = (k == steps - 1) ? s[k] : __dadd_rn(s[k], run);
+        s[k] = run;
+    }
+    const double mean = __ddiv_rn(s[0], (double)n);
+    for (int k = 0; k < steps; ++k)
+        s[k] = __ddiv_rn(__ddiv_rn(s[k], (double)(n - cuts.v[k])), mean);
+}
+
+// row_norm_sum[k] += sum over rows, in row order
+__global__ void accumulate_kernel(const double* norm, int rows, int steps,
+                                  double* row_norm_sum) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= steps) return;
+    double a = row_norm_sum[k];
+    for (int r = 0; r < rows; ++r) a = __dadd_rn(a, norm[(long long)r * steps + k]);
+    row_norm_sum[k] = a;
+}
+
+__global__ void finish_kernel(const double* row_norm_sum, int steps,
+                              double total_rows, float* curve) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < steps) curve[k] = (float)__ddiv_rn(row_norm_sum[k], total_rows);
+}
+
+__global__ void ause_kernel(const float* oracle, const float* pred, int steps,
+                            float* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double a = 0.0;
+    for (int k = 0; k < steps; ++k)
+        a = __dadd_rn(a, (double)__fsub_rn(pred[k], oracle[k]));
+    *out = (float)__ddiv_rn(a, (double)steps);
+}
+
+// ---- host ----------------------------------------------------------------
+struct SparsLayout {
+    size_t keys[2], vals[2], idx[2], counts, seg, total;
+    int n, ntiles;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static SparsLayout layout(int rows, int H, int W, int k, bool with_idx) {
+    SparsLayout L;
+    L.n = (H - k + 1) * (W - k + 1);
+    L.ntiles = (L.n + SORT_TILE - 1) / SORT_TILE;
+    const size_t e = (size_t)rows * L.n;
+    size_t off = 0;
+    for (int i = 0; i < 2; ++i) { L.keys[i] = off; off = align_up(off + e * 4); }
+    for (int i = 0; i < 2; ++i) { L.vals[i] = off; off = align_up(off + e * 4); }
+    for (int i = 0; i < 2; ++i) {
+        L.idx[i] = off;
+        if (with_idx) off = align_up(off + e * 4);
+    }
+    L.counts = off; off = align_up(off + (size_t)rows * RADIX * L.ntiles * 4);
+    L.seg = off; off = align_up(off + (size_t)rows * USL_MAX_STEPS * 8);
+    L.total = off;
+    return L;
+}
+
+static unsigned flat_grid(long long total) {
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace usl
+
+using namespace usl;
+
+extern "C" size_t usl_spars_workspace_bytes(int rows, int H, int W, int k,
+                                            int with_order) {
+    if (rows <= 0 || k < 1 || H < k || W < k) return 0;
+    return layout(rows, H, W, k, with_order != 0).total;
+}
+
+extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
+                               int rows, int H, int W, int k, const int* cuts,
+                               int steps, double* row_norm_sum,
+                               int32_t* order_out, float* pooled_oracle_out,
+                               float* pooled_pred_out, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+    if (!oracle || !predicted || !cuts || !row_norm_sum || !workspace ||
+        rows <= 0 || steps < 1)
+        return USL_ERR_ARG;
+    if (k < 1 || k > KMAX || H < k || W < k || steps > USL_MAX_STEPS)
+        return USL_ERR_UNSUPPORTED;
+    if ((long long)rows * (H - k + 1) * (W - k + 1) >= (1ll << 31))
+        return USL_ERR_UNSUPPORTED;
+    const bool with_idx = order_out != nullptr;
+    const SparsLayout L = layout(rows, H, W, k, with_idx);
+    if (workspace_bytes < L.total) return USL_ERR_WORKSPACE;
+    Cuts c;
+    for (int i = 0; i <= steps; ++i) {
+        c.v[i] = cuts[i];
+        if (cuts[i] < 0 || cuts[i] > L.n || (i && cuts[i] < cuts[i - 1]))
+            return USL_ERR_ARG;
+    }
+    if (c.v[steps] != L.n) return USL_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    char* ws = (char*)workspace;
+    unsigned* keys[2] = {(unsigned*)(ws + L.keys[0]), (unsigned*)(ws + L.keys[1])};
+    float* vals[2] = {(float*)(ws + L.vals[0]), (float*)(ws + L.vals[1])};
+    int* idx[2] = {(int*)(ws + L.idx[0]), (int*)(ws + L.idx[1])};
+    unsigned* counts = (unsigned*)(ws + L.counts);
+    double* seg = (double*)(ws + L.seg);
+    const int n = L.n, ntiles = L.ntiles;
+
+    const long long pool_threads =
+        (long long)rows * (H - k + 1) * ((W - k + 1 + PX - 1) / PX);
+    pool_kernel<<<flat_grid(pool_threads), 256, 0, stream>>>(
+        oracle, rows, H, W, k, vals[0], nullptr);
+    pool_kernel<<<flat_grid(pool_threads), 256, 0, stream>>>(
+        predicted, rows, H, W, k, pooled_pred_out, keys[0]);
+    if (pooled_oracle_out)
+        if (cudaMemcpyAsync(pooled_oracle_out, vals[0], (size_t)rows * n * 4,
+                            cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+            return USL_ERR_CUDA;
+    if (with_idx)
+        iota_kernel<<<flat_grid((long long)rows * n), 256, 0, stream>>>(
+            idx[0], rows, n);
+    const dim3 grid(ntiles, rows);
+    int cur = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = pass * 8;
+        hist_kernel<<<grid, SORT_THREADS, 0, stream>>>(keys[cur], n, ntiles,
+                                                       shift, counts);
+        scan_kernel<<<rows, 1024, 0, stream>>>(counts, RADIX * ntiles);
+        if (with_idx)
+            scatter_kernel<true><<<grid, SORT_THREADS, 0, stream>>>(
+                keys[cur], vals[cur], idx[cur], keys[cur ^ 1], vals[cur ^ 1],
+                idx[cur ^ 1], counts, n, ntiles, shift);
+        else
+            scatter_kernel<false><<<grid, SORT_THREADS, 0, stream>>>(
+                keys[cur], vals[cur], nullptr, keys[cur ^ 1], vals[cur ^ 1],
+                nullptr, counts, n, ntiles, shift);
+        cur ^= 1;
+    }
+    if (with_idx)
+        if (cudaMemcpyAsync(order_out, idx[cur], (size_t)rows * n * 4,
+                            cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+            return USL_ERR_CUDA;
+    segment_kernel<<<dim3(steps, rows), SEG_LANES, 0, stream>>>(vals[cur], n, c,
+                                                               steps, seg);
+    row_norm_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(seg, rows, n, c, steps);
+    accumulate_kernel<<<(steps + 127) / 128, 128, 0, stream>>>(seg, rows, steps,
+                                                              row_norm_sum);
+    return check_launch();
+}
+
+extern "C" int usl_spars_finish(const double* row_norm_sum, int steps,
+                                long long total_rows, float* curve,
+                                void* stream) {
+    if (!row_norm_sum || !curve || steps < 1 || total_rows < 1) return USL_ERR_ARG;
+    finish_kernel<<<(steps + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        row_norm_sum, steps, (double)total_rows, curve);
+    return check_launch();
+}
+
+extern "C" int usl_spars_ause(const float* oracle_curve, const float* pred_curve,
+                              int steps, float* out, void* stream) {
+    if (!oracle_curve || !pred_curve || !out || steps < 1) return USL_ERR_ARG;
+    ause_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(oracle_curve, pred_curve,
+                                                    steps, out);
+    return check_launch();
+}

@@ -1,0 +1,476 @@
+"""Host side of the hot path: tensors -> C ABI structs -> libusl launches,
+wrapped as `torch.autograd.Function`s.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all
+arithmetic happens in the CUDA kernels behind `_lib.lib()`.  Inputs must be
+CUDA fp32 tensors: there is no CPU fallback.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import (LOSS_TYPES, TERM_CONS_D, TERM_CONS_U, TERM_REPROJ,
+                   TERM_SMOOTH_D, TERM_SMOOTH_U, TERM_UNC, USL_NUM_TERMS,
+                   UslLossConfig, UslLossScale, check, lib)
+
+
+# --------------------------------------------------------------------------
+# tensor plumbing
+# --------------------------------------------------------------------------
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda_f32(t: Tensor, name: str) -> None:
+    if not isinstance(t, Tensor):
+        raise TypeError(f'{name} must be a torch.Tensor')
+    if t.dtype != torch.float32:
+        raise TypeError(f'{name} must be float32, got {t.dtype}')
+    if not t.is_cuda:
+        raise ValueError(f'{name} must be a CUDA tensor: the B200 loss path '
+                         'has no CPU fallback')
+
+
+def planes(t: Tensor) -> Tensor:
+    """A view/copy of a (B,C,h,w) tensor whose h*w planes are contiguous."""
+    if t.dim() != 4:
+        raise ValueError(f'expected a 4-d tensor, got shape {tuple(t.shape)}')
+    h, w = t.shape[-2:]
+    if t.stride(3) == 1 and t.stride(2) == w:
+        return t
+    return t.contiguous()
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _strides(t: Optional[Tensor]) -> Tuple[int, int]:
+    if t is None:
+        return 0, 0
+    return t.stride(0), t.stride(1)
+
+
+# --------------------------------------------------------------------------
+# loss configuration -> per-scale term masks and coefficients
+# --------------------------------------------------------------------------
+@dataclass(frozen=True)
+class LossSettings:
+    """The scalars of `config.yml`'s `loss:` block that the kernels need
+    (reference: train/loss.py:438-447 and 357-360)."""
+    wssim_weight: float = 1.0
+    consistency_weight: float = 1.0
+    smoothness_weight: float = 1.0
+    predictive_error_weight: float = 1.0
+    alpha: float = 0.85
+    c1: float = 0.01 ** 2
+    c2: float = 0.03 ** 2
+    loss_type: str = 'l1'
+    err_smoothness_weight: float = 1.0
+    err_consistency_weight: float = 1.0
+
+    def terms(self) -> int:
+        t = TERM_REPROJ | TERM_CONS_D | TERM_SMOOTH_D | TERM_UNC
+        if self.err_smoothness_weight > 0:      # loss.py:428
+            t |= TERM_SMOOTH_U
+        if self.err_consistency_weight > 0:     # loss.py:430
+            t |= TERM_CONS_U
+        return t
+
+    def coefs(self, scale_index: int, n_pixels: int,
+              n_unc: Optional[int] = None) -> List[float]:
+        """coef[k] * (raw sum k) = contribution of term k at this scale.
+
+        n_pixels = B*h*w of the (global) batch: every mean of the reference
+        (loss.py:151,185-186,264,393-403) is a sum divided by it (or by twice
+        it for the two-channel uncertainty mean).  n_unc is the pixel count of
+        the error terms when they run on pooled maps."""
+        n = float(n_pixels)
+        nu = float(n_unc if n_unc is not None else n_pixels)
+        pe = self.predictive_error_weight
+        half = 0.5 if self.loss_type == 'log_bayesian' else 1.0
+        return [self.wssim_weight / n,
+                self.consistency_weight / n,
+                self.smoothness_weight / (n * 2 ** scale_index),
+                pe * half / (2.0 * nu),
+                pe * self.err_smoothness_weight / nu,
+                pe * self.err_consistency_weight / nu]
+
+
+def make_config(terms: int, settings: LossSettings,
+                coefs: Sequence[float]) -> UslLossConfig:
+    cfg = UslLossConfig()
+    cfg.terms = terms
+    cfg.loss_type = LOSS_TYPES[settings.loss_type]
+    cfg.alpha, cfg.c1, cfg.c2 = settings.alpha, settings.c1, settings.c2
+    for k in range(USL_NUM_TERMS):
+        cfg.coef[k] = coefs[k]
+    return cfg
+
+
+def make_scale(images: Optional[Tensor], disp: Optional[Tensor],
+               unc: Optional[Tensor], *, shape: Tuple[int, int, int],
+               recon_in: Optional[Tensor] = None,
+               err_in: Optional[Tensor] = None,
+               recon_out: Optional[Tensor] = None,
+               err_out: Optional[Tensor] = None,
+               grad_recon_in: Optional[Tensor] = None,
+               grad_disp: Optional[Tensor] = None,
+               grad_unc: Optional[Tensor] = None,
+               grad_recon_out: Optional[Tensor] = None) -> UslLossScale:
+    s = UslLossScale()
+    s.B, s.h, s.w = shape
+    s.images = _ptr(images); s.img_bs, s.img_cs = _strides(images)
+    s.disp = _ptr(disp); s.disp_bs, s.disp_cs = _strides(disp)
+    s.unc = _ptr(unc); s.unc_bs, s.unc_cs = _strides(unc)
+    s.recon_in = _ptr(recon_in); s.rin_bs, s.rin_cs = _strides(recon_in)
+    s.err_in = _ptr(err_in); s.ein_bs, s.ein_cs = _strides(err_in)
+    s.recon_out = _ptr(recon_out)
+    s.err_out = _ptr(err_out)
+    s.grad_recon_in = _ptr(grad_recon_in)
+    s.grad_disp = _ptr(grad_disp); s.gd_bs, s.gd_cs = _strides(grad_disp)
+    s.grad_unc = _ptr(grad_unc); s.gu_bs, s.gu_cs = _strides(grad_unc)
+    s.grad_recon_out = _ptr(grad_recon_out)
+    return s
+
+
+def _array(cls, items):
+    arr = (cls * len(items))()
+    for i, it in enumerate(items):
+        arr[i] = it
+    return arr
+
+
+# --------------------------------------------------------------------------
+# launches
+# --------------------------------------------------------------------------
+def loss_forward(cfgs: Sequence[UslLossConfig],
+                 scales: Sequence[UslLossScale], device,
+                 reduce_group=None) -> Tuple[Tensor, Tensor, Tensor]:
+    """One fused forward launch over all scales.
+
+    Returns (disp_loss, error_loss, sums): two 0-dim fp32 tensors and the
+    fp64[n_scales, 6] raw per-term sums (all-reduced over `reduce_group` when
+    the batch is sharded over ranks)."""
+    L = lib()
+    n = len(scales)
+    counts = []
+    for s in scales:
+        c = L.usl_loss_fwd_ctas(C.byref(s))
+        if c < 0:
+            check(c, 'usl_loss_fwd_ctas')
+        counts.append(c)
+    starts = [0]
+    for c in counts:
+        starts.append(starts[-1] + c)
+    partials = torch.empty(starts[-1] * USL_NUM_TERMS, dtype=torch.float32,
+                           device=device)
+    sums = torch.empty(n, USL_NUM_TERMS, dtype=torch.float64, device=device)
+    out_disp = torch.empty((), dtype=torch.float32, device=device)
+    out_err = torch.empty((), dtype=torch.float32, device=device)
+    coef = coef_tensor(tuple(tuple(c.coef) for c in cfgs), device)
+    stream = _stream(partials)
+    cfg_arr, sc_arr = _array(UslLossConfig, cfgs), _array(UslLossScale, scales)
+    check(L.usl_loss_fwd(cfg_arr, sc_arr, n, partials.data_ptr(), stream),
+          'usl_loss_fwd')
+    check(L.usl_loss_reduce(partials.data_ptr(), (C.c_int * (n + 1))(*starts),
+                            n, sums.data_ptr(), stream), 'usl_loss_reduce')
+    if reduce_group is not None:
+        torch.distributed.all_reduce(sums, group=reduce_group)
+    check(L.usl_loss_combine(sums.data_ptr(), coef.data_ptr(), n,
+                             out_disp.data_ptr(), out_err.data_ptr(), stream),
+          'usl_loss_combine')
+    return out_disp, out_err, sums
+
+
+_COEF_CACHE = {}
+
+
+def coef_tensor(coefs, device) -> Tensor:
+    """Device copy of the per-scale coefficient table (cached: one H2D copy per
+    distinct configuration/shape, not per step)."""
+    key = (coefs, str(device))
+    t = _COEF_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(coefs, dtype=torch.float32, device=device)
+        if len(_COEF_CACHE) > 256:
+            _COEF_CACHE.clear()
+        _COEF_CACHE[key] = t
+    return t
+
+
+def loss_backward(cfgs: Sequence[UslLossConfig],
+                  scales: Sequence[UslLossScale], g_disp: Optional[Tensor],
+                  g_err: Optional[Tensor], device, stages: int = 3) -> None:
+    L = lib()
+    stream = torch.cuda.current_stream(device).cuda_stream
+    check(L.usl_loss_bwd(_array(UslLossConfig, cfgs),
+                         _array(UslLossScale, scales), len(scales),
+                         _ptr(g_disp), _ptr(g_err), stages, stream),
+          'usl_loss_bwd')
+
+
+def pyramid(x: Tensor, scales: int) -> List[Tensor]:
+    """train/utils.py:27-50.  Level 0 is `x` itself (the reference's level 0
+    is a bit-identical copy); levels >= 1 come from one launch."""
+    require_cuda_f32(x, 'x')
+    x = planes(x)
+    b, c, h, w = x.shape
+    if scales < 1 or scales > _lib.USL_MAX_SCALES:
+        raise ValueError(f'scales must be in [1, {_lib.USL_MAX_SCALES}]')
+    out = [x]
+    for i in range(1, scales):
+        if (h >> i) < 1 or (w >> i) < 1:
+            raise ValueError('image too small for the requested scales')
+        out.append(torch.empty(b, c, h >> i, w >> i, dtype=x.dtype,
+                               device=x.device))
+    ptrs = (C.c_void_p * scales)(*[t.data_ptr() for t in out])
+    check(lib().usl_pyramid(x.data_ptr(), b, c, h, w, x.stride(0), x.stride(1),
+                            scales, ptrs, _stream(x)), 'usl_pyramid')
+    return out
+
+
+def warp_forward(disp: Tensor, sign: float, image: Tensor,
+                 out: Tensor) -> None:
+    b, c, h, w = image.shape
+    check(lib().usl_warp_fwd(disp.data_ptr(), disp.stride(0), sign,
+                             image.data_ptr(), image.stride(0),
+                             image.stride(1), b, c, h, w, out.data_ptr(),
+                             out.stride(0), out.stride(1), _stream(image)),
+          'usl_warp_fwd')
+
+
+def warp_backward_disp(disp: Tensor, sign: float, image: Tensor,
+                       grad_out: Tensor, grad_disp: Tensor) -> None:
+    b, c, h, w = image.shape
+    check(lib().usl_warp_bwd_disp(
+        disp.data_ptr(), disp.stride(0), sign, image.data_ptr(),
+        image.stride(0), image.stride(1), grad_out.data_ptr(),
+        grad_out.stride(0), grad_out.stride(1), b, c, h, w,
+        grad_disp.data_ptr(), grad_disp.stride(0), _stream(image)),
+        'usl_warp_bwd_disp')
+
+
+class Reconstruct(torch.autograd.Function):
+    """train/utils.py:65-109 as one op: out = warp(image; sign * disp).
+
+    Differentiable w.r.t. the disparity (a deterministic gather).  The
+    gradient w.r.t. the sampled image is not provided by this op: on the
+    training path the sampled image is data, and the consistency terms -- the
+    only place the reference differentiates through the sampled map -- are
+    handled inside the fused loss."""
+
+    @staticmethod
+    def forward(ctx, disp: Tensor, image: Tensor, sign: float) -> Tensor:
+        require_cuda_f32(disp, 'disparity')
+        require_cuda_f32(image, 'opposite_image')
+        if disp.dim() != 4 or disp.size(1) != 1 or \
+                disp.shape[-2:] != image.shape[-2:] or \
+                disp.size(0) != image.size(0):
+            raise ValueError('disparity must be (B,1,h,w) matching the image')
+        disp, image = planes(disp), planes(image)
+        out = torch.empty(image.shape, dtype=image.dtype, device=image.device)
+        warp_forward(disp, sign, image, out)
+        ctx.sign = sign
+        ctx.save_for_backward(disp, image)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        disp, image = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError(
+                'gradient w.r.t. the sampled image of a stand-alone '
+                'reconstruct() is not implemented; use ConsistencyLoss')
+        grad_disp = None
+        if ctx.needs_input_grad[0]:
+            grad_out = planes(grad_out)
+            grad_disp = torch.empty_like(disp, memory_format=torch.contiguous_format)
+            warp_backward_disp(disp, ctx.sign, image, grad_out, grad_disp)
+        return grad_disp, None, None
+
+
+class ReconstructPair(torch.autograd.Function):
+    """One level of train/utils.py:112-135: (B,6,h,w) reconstruction of both
+    views from prediction[:, :2] and the stereo pair, written straight into one
+    buffer (no torch.cat)."""
+
+    @staticmethod
+    def forward(ctx, pred: Tensor, images: Tensor) -> Tensor:
+        require_cuda_f32(pred, 'disparity')
+        require_cuda_f32(images, 'pyramid level')
+        if images.size(1) != 6 or pred.size(1) < 2:
+            raise ValueError('expected (B,6,h,w) images and >=2 disparity '
+                             'channels')
+        pred, images = planes(pred), planes(images)
+        out = torch.empty(images.shape, dtype=images.dtype,
+                          device=images.device)
+        warp_forward(pred[:, 0:1], -1.0, images[:, 3:6], out[:, 0:3])
+        warp_forward(pred[:, 1:2], 1.0, images[:, 0:3], out[:, 3:6])
+        ctx.save_for_backward(pred, images)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        pred, images = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError('images are data on this path')
+        grad_pred = None
+        if ctx.needs_input_grad[0]:
+            grad_out = planes(grad_out)
+            grad_pred = torch.zeros_like(pred,
+                                         memory_format=torch.contiguous_format)
+            warp_backward_disp(pred[:, 0:1], -1.0, images[:, 3:6],
+                               grad_out[:, 0:3], grad_pred[:, 0:1])
+            warp_backward_disp(pred[:, 1:2], 1.0, images[:, 0:3],
+                               grad_out[:, 3:6], grad_pred[:, 1:2])
+        return grad_pred, None
+
+
+class Pool3(torch.autograd.Function):
+    """3x3 valid mean (train/loss.py:386-387) and its transpose."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor) -> Tensor:
+        require_cuda_f32(x, 'x')
+        x = planes(x)
+        b, c, h, w = x.shape
+        out = torch.empty(b, c, h - 2, w - 2, dtype=x.dtype, device=x.device)
+        check(lib().usl_pool3_fwd(x.data_ptr(), x.stride(0), x.stride(1), b, c,
+                                  h, w, out.data_ptr(), _stream(x)),
+              'usl_pool3_fwd')
+        ctx.shape = (b, c, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        b, c, h, w = ctx.shape
+        grad_out = grad_out.contiguous()
+        gx = torch.empty(b, c, h, w, dtype=grad_out.dtype,
+                         device=grad_out.device)
+        check(lib().usl_pool3_bwd(grad_out.data_ptr(), b, c, h, w,
+                                  gx.data_ptr(), _stream(gx)), 'usl_pool3_bwd')
+        return gx
+
+
+# --------------------------------------------------------------------------
+# the fused multi-scale loss as one autograd node
+# --------------------------------------------------------------------------
+@dataclass
+class ScaleSpec:
+    """What one scale of a fused call consists of: indices into the flat
+    tensor argument list of `FusedLoss.apply` (-1 = absent) and, for the
+    two-channel disparity / uncertainty maps, the first channel inside that
+    tensor (so a (B,4,h,w) prediction is passed once, without slicing)."""
+    terms: int
+    coefs: Tuple[float, ...]
+    images: int = -1
+    disp: int = -1
+    disp_ch: int = 0
+    unc: int = -1
+    unc_ch: int = 0
+    recon: int = -1         # given reconstruction (B,6,h,w)
+    err: int = -1           # given error map (B,2,h,w)
+    want_err: bool = False  # also return the (B,2,h,w) error map
+
+
+def _pair(t: Tensor, ch: int) -> Tensor:
+    return t[:, ch:ch + 2]
+
+
+class FusedLoss(torch.autograd.Function):
+    """forward(settings, specs, group, *tensors) ->
+           (disp_loss, error_loss, sums[n,6], error maps that were asked for...)
+
+    Gradients are produced for the disparity / uncertainty tensors and for
+    given reconstructions; images and given error maps are data
+    (loss.py:418 detaches the error)."""
+
+    @staticmethod
+    def forward(ctx, settings: LossSettings, specs: Sequence[ScaleSpec],
+                group, *tensors: Tensor):
+        for i, t in enumerate(tensors):
+            require_cuda_f32(t, f'tensor {i}')
+        tensors = tuple(planes(t) for t in tensors)
+        device = tensors[0].device
+        cfgs, scales, errs = [], [], []
+        for sp in specs:
+            b, h, w = _spec_shape(sp, tensors)
+            err_out = None
+            if sp.want_err:
+                err_out = torch.empty(b, 2, h, w, dtype=torch.float32,
+                                      device=device)
+                errs.append(err_out)
+            cfgs.append(make_config(sp.terms, settings, sp.coefs))
+            scales.append(make_scale(
+                tensors[sp.images] if sp.images >= 0 else None,
+                _pair(tensors[sp.disp], sp.disp_ch) if sp.disp >= 0 else None,
+                _pair(tensors[sp.unc], sp.unc_ch) if sp.unc >= 0 else None,
+                shape=(b, h, w),
+                recon_in=tensors[sp.recon] if sp.recon >= 0 else None,
+                err_in=tensors[sp.err] if sp.err >= 0 else None,
+                err_out=err_out))
+        out_disp, out_err, sums = loss_forward(cfgs, scales, device, group)
+        ctx.settings, ctx.specs = settings, specs
+        ctx.save_for_backward(*tensors)
+        ctx.mark_non_differentiable(sums, *errs)
+        ctx.set_materialize_grads(False)
+        return (out_disp, out_err, sums) + tuple(errs)
+
+    @staticmethod
+    def backward(ctx, g_disp, g_err, *unused):
+        tensors = ctx.saved_tensors
+        specs, settings = ctx.specs, ctx.settings
+        device = tensors[0].device
+        if g_disp is not None:
+            g_disp = g_disp.contiguous()
+        if g_err is not None:
+            g_err = g_err.contiguous()
+        # which channels of each tensor the kernels will fully overwrite
+        covered = [set() for _ in tensors]
+        for sp in specs:
+            if sp.disp >= 0:
+                covered[sp.disp].update((sp.disp_ch, sp.disp_ch + 1))
+            if sp.unc >= 0:
+                covered[sp.unc].update((sp.unc_ch, sp.unc_ch + 1))
+            if sp.recon >= 0:
+                covered[sp.recon].update(range(6))
+        grads: List[Optional[Tensor]] = [None] * len(tensors)
+        for i, t in enumerate(tensors):
+            if not covered[i]:
+                continue
+            alloc = torch.empty_like if len(covered[i]) == t.size(1) \
+                else torch.zeros_like
+            grads[i] = alloc(t, memory_format=torch.contiguous_format)
+        cfgs, scales = [], []
+        for sp in specs:
+            b, h, w = _spec_shape(sp, tensors)
+            cfgs.append(make_config(sp.terms, settings, sp.coefs))
+            scales.append(make_scale(
+                tensors[sp.images] if sp.images >= 0 else None,
+                _pair(tensors[sp.disp], sp.disp_ch) if sp.disp >= 0 else None,
+                _pair(tensors[sp.unc], sp.unc_ch) if sp.unc >= 0 else None,
+                shape=(b, h, w),
+                recon_in=tensors[sp.recon] if sp.recon >= 0 else None,
+                err_in=tensors[sp.err] if sp.err >= 0 else None,
+                grad_disp=_pair(grads[sp.disp], sp.disp_ch)
+                if sp.disp >= 0 else None,
+                grad_unc=_pair(grads[sp.unc], sp.unc_ch)
+                if sp.unc >= 0 else None,
+                grad_recon_out=grads[sp.recon] if sp.recon >= 0 else None))
+        loss_backward(cfgs, scales, g_disp, g_err, device)
+        needs = ctx.needs_input_grad[3:]
+        return (None, None, None) + tuple(
+            g if need else None for g, need in zip(grads, needs))
+
+
+def _spec_shape(sp: ScaleSpec, tensors) -> Tuple[int, int, int]:
+    for idx in (sp.images, sp.disp, sp.unc, sp.err):
+        if idx >= 0:
+            b, _, h, w = tensors[idx].shape
+            return b, h, w
+    raise ValueError('empty scale spec')
