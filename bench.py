@@ -415,6 +415,17 @@ def kernel_times(K, U, fn, sets, dev, reps):
         prepared[i % nsets][2], prepared[i % nsets][4], one, one, dev, 1))
     out['loss_bwd_main'] = t(lambda i: K.loss_backward(
         prepared[i % nsets][2], prepared[i % nsets][4], one, one, dev, 2))
+    # the training step's path: sums + gradients in one pass (scatter kernel,
+    # marching kernel in GRAD mode, reduce, combine)
+    try:
+        out['loss_onepass'] = t(lambda i: K.loss_forward(
+            prepared[i % nsets][2], prepared[i % nsets][4], dev,
+            with_grad=True))
+        out['loss_onepass_main'] = out['loss_onepass'] - \
+            out['loss_bwd_scatter'] - (out['loss_fwd'] - out['loss_fwd_main']
+                                       if 'loss_fwd_main' in out else 0.0)
+    except Exception as e:      # not eligible for this workload
+        out['loss_onepass'] = None
     return out
 
 

@@ -110,11 +110,25 @@ typedef struct UslLossScale {
 /* All pyramid scales of a step are processed by ONE launch: `cfgs` and
  * `scales` are HOST arrays of n_scales entries (largest scale first).
  *
- * number of CTAs (= rows of `partials`, USL_NUM_TERMS floats each) the forward
- * launch uses for one scale; <0 on error. */
+ * Two kernel families sit behind these entry points.  The register-marching
+ * kernels (csrc/march_core.cuh) take every call whose scales all warp
+ * in-kernel (no recon_in / err_in), have the reprojection term on and an even
+ * width -- the training step; everything else (given reconstructions or error
+ * maps, stand-alone terms, odd widths) runs on the general strip kernels
+ * (csrc/loss_core.cuh).
+ *
+ * usl_loss_plan: row offsets into `partials` (USL_NUM_TERMS floats per row) of
+ * every scale for a launch in `mode`: cta_starts[n_scales + 1] (HOST).
+ * USL_MODE_GRAD is the one-pass sums+gradient launch (usl_loss_grad); it
+ * returns USL_ERR_UNSUPPORTED when the call does not qualify for it. */
+#define USL_MODE_FWD 0
+#define USL_MODE_GRAD 1
+int usl_loss_plan(const UslLossConfig* cfgs, const UslLossScale* scales,
+                  int n_scales, int mode, int* cta_starts);
+/* (legacy) rows the general forward kernel uses for one scale; <0 on error. */
 int usl_loss_fwd_ctas(const UslLossScale* s);
-/* forward: per-CTA partial sums of the enabled terms -> partials (scale-major,
- * scale i starting at row sum_{j<i} usl_loss_fwd_ctas(scales[j])). */
+/* forward: partial sums of the enabled terms -> partials (scale-major, scale i
+ * starting at row cta_starts[i] of usl_loss_plan(USL_MODE_FWD)). */
 int usl_loss_fwd(const UslLossConfig* cfgs, const UslLossScale* scales,
                  int n_scales, float* partials, void* stream);
 /* fixed-order fp64 reduction of the partials -> sums[n_scales][6] (device).
@@ -138,6 +152,20 @@ int usl_loss_bwd(const UslLossConfig* cfgs, const UslLossScale* scales,
 #define USL_BWD_STAGE_SCATTER 1
 #define USL_BWD_STAGE_MAIN 2
 #define USL_BWD_STAGE_ALL 3
+/* forward AND backward in one pass over the inputs (the backward needs every
+ * forward intermediate anyway): writes the partial sums (rows per
+ * usl_loss_plan(USL_MODE_GRAD); `partials` may be NULL) and grad_disp /
+ * grad_unc of every scale, scaled by the upstream gradients gout_* (device
+ * scalars; NULL = 1).  The training loop back-propagates disp_loss +
+ * error_loss (reference train.py:126-128), i.e. both upstream gradients are 1:
+ * the host runs this in `forward` with gout = NULL and, in `backward`, calls it
+ * again with the real upstream gradients and USL_GRAD_SKIP_IF_UNIT -- every
+ * CTA then returns at once if they are both 1 (nothing to redo), and
+ * recomputes the gradients otherwise.  No host synchronisation either way. */
+#define USL_GRAD_SKIP_IF_UNIT 1
+int usl_loss_grad(const UslLossConfig* cfgs, const UslLossScale* scales,
+                  int n_scales, const float* gout_disp, const float* gout_err,
+                  float* partials, int flags, void* stream);
 
 /* 3x3 valid mean (loss.py:386-387, `pooling=True`) and its transpose. */
 int usl_pool3_fwd(const float* x, long long x_bs, long long x_cs, int B, int C,

@@ -77,35 +77,49 @@ extern "C" int emu_loss_fwd(const UslLossConfig* cfg, const UslLossScale* s,
     return 0;
 }
 
+static void run_scatter(const LossParams& P, int consR, const float* gout) {
+    ConsParams C = {};
+    C.B = P.B; C.h = P.h; C.w = P.w;
+    C.disp = P.disp; C.d_bs = P.d_bs; C.d_cs = P.d_cs;
+    C.unc = P.unc; C.u_bs = P.u_bs; C.u_cs = P.u_cs;
+    C.gout_d = gout; C.gout_e = gout + 1;
+    C.grad_disp = P.grad_disp; C.gd_bs = P.gd_bs; C.gd_cs = P.gd_cs;
+    C.terms = P.terms & (TERM_CONS_D | TERM_CONS_U);
+    C.coef_dd = P.coef[ACC_CONS_D]; C.coef_ud = P.coef[ACC_CONS_U];
+    C.R = consR > C.h ? C.h : consR;
+    std::vector<float> arena(cons_ring_floats(C.w));
+    for (int b = 0; b < C.B; ++b)
+        for (int ya = 0; ya < C.h; ya += C.R) {
+            for (auto& v : arena) v = NAN;
+            ConsTile T;
+            T.b = b; T.ya = ya; T.yb = ya + C.R < C.h ? ya + C.R : C.h;
+            const ConsRings S = cons_carve(C.w, arena.data());
+            for (int r = cons_first_step(T); r <= cons_last_step(T); ++r) {
+                cons_phase_A(C, T, S, r, 0, 1);
+                cons_phase_B(C, T, S, r, 0, 1, gout[0], gout[1]);
+                cons_phase_C_host(C, S, r);
+                cons_phase_D(C, T, S, r, 0, 1);
+            }
+        }
+}
+
+// The transposed warp of the consistency terms alone (pure store into
+// grad_disp); the marching emulation adds the rest on top of it.
+extern "C" int emu_cons_scatter(const UslLossConfig* cfg, const UslLossScale* s,
+                                int consR, const float* gout) {
+    LossParams P;
+    to_params(cfg, s, 16, 16, &P);
+    if (P.terms & (TERM_CONS_D | TERM_CONS_U)) run_scatter(P, consR, gout);
+    return 0;
+}
+
 extern "C" int emu_loss_bwd(const UslLossConfig* cfg, const UslLossScale* s,
                             int TW, int R, int consR, const float* gout) {
     LossParams P;
     to_params(cfg, s, TW, R, &P);
     P.gout_d = gout; P.gout_e = gout + 1;
     if (P.terms & (TERM_CONS_D | TERM_CONS_U)) {
-        ConsParams C = {};
-        C.B = P.B; C.h = P.h; C.w = P.w;
-        C.disp = P.disp; C.d_bs = P.d_bs; C.d_cs = P.d_cs;
-        C.unc = P.unc; C.u_bs = P.u_bs; C.u_cs = P.u_cs;
-        C.gout_d = gout; C.gout_e = gout + 1;
-        C.grad_disp = P.grad_disp; C.gd_bs = P.gd_bs; C.gd_cs = P.gd_cs;
-        C.terms = P.terms & (TERM_CONS_D | TERM_CONS_U);
-        C.coef_dd = P.coef[ACC_CONS_D]; C.coef_ud = P.coef[ACC_CONS_U];
-        C.R = consR > C.h ? C.h : consR;
-        std::vector<float> arena(cons_ring_floats(C.w));
-        for (int b = 0; b < C.B; ++b)
-            for (int ya = 0; ya < C.h; ya += C.R) {
-                for (auto& v : arena) v = NAN;
-                ConsTile T;
-                T.b = b; T.ya = ya; T.yb = ya + C.R < C.h ? ya + C.R : C.h;
-                const ConsRings S = cons_carve(C.w, arena.data());
-                for (int r = cons_first_step(T); r <= cons_last_step(T); ++r) {
-                    cons_phase_A(C, T, S, r, 0, 1);
-                    cons_phase_B(C, T, S, r, 0, 1, gout[0], gout[1]);
-                    cons_phase_C_host(C, S, r);
-                    cons_phase_D(C, T, S, r, 0, 1);
-                }
-            }
+        run_scatter(P, consR, gout);
         P.grad_disp_accumulate = 1;
     }
     run_main<true>(P, gout, nullptr);

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, 'libusl.so')
 
 USL_NUM_TERMS = 6
 USL_MAX_SCALES = 8
+USL_ERR_UNSUPPORTED = -3
 
 TERM_REPROJ, TERM_CONS_D, TERM_SMOOTH_D = 1, 2, 4
 TERM_UNC, TERM_SMOOTH_U, TERM_CONS_U = 8, 16, 32
@@ -58,6 +59,12 @@ SIGNATURES = {
                                     C.c_longlong, C.c_longlong, C.c_int,
                                     C.c_int, C.c_int, C.c_int, _f32p,
                                     C.c_longlong, C.c_void_p]),
+    'usl_loss_plan': (C.c_int, [C.POINTER(UslLossConfig),
+                                C.POINTER(UslLossScale), C.c_int, C.c_int,
+                                C.POINTER(C.c_int)]),
+    'usl_loss_grad': (C.c_int, [C.POINTER(UslLossConfig),
+                                C.POINTER(UslLossScale), C.c_int, _f32p, _f32p,
+                                _f32p, C.c_int, C.c_void_p]),
     'usl_loss_fwd_ctas': (C.c_int, [C.POINTER(UslLossScale)]),
     'usl_loss_fwd': (C.c_int, [C.POINTER(UslLossConfig),
                                C.POINTER(UslLossScale), C.c_int, _f32p,

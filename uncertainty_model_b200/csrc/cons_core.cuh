@@ -31,7 +31,8 @@ struct ConsParams {
     const float* disp; long long d_bs, d_cs;
     const float* unc;  long long u_bs, u_cs;
     const float* gout_d;                     // device scalars: upstream grads
-    const float* gout_e;                     // (NULL = 0)
+    const float* gout_e;                     // (NULL = gout_default)
+    float gout_default;
     float* grad_disp; long long gd_bs, gd_cs;  // pure store, both planes
     unsigned terms;                          // TERM_CONS_D | TERM_CONS_U
     float coef_dd, coef_ud;

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include "cons_core.cuh"
+#include "march_launch.cuh"
 #include "usl_common.cuh"
 
 namespace usl {
@@ -25,6 +26,7 @@ struct MultiCons {
     int cta_start[USL_MAX_SCALES + 1];
     int strips[USL_MAX_SCALES];
     int n;
+    int skip_if_unit;   // return at once when both upstream gradients are 1
 };
 
 template <bool BWD>
@@ -128,8 +130,9 @@ cons_scatter_kernel(const __grid_constant__ MultiCons M) {
     const ConsRings S = cons_carve(P.w, reinterpret_cast<float*>(smem_raw));
     const int tid = threadIdx.x, nt = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const float gd_up = P.gout_d ? __ldg(P.gout_d) : 0.0f;
-    const float ge_up = P.gout_e ? __ldg(P.gout_e) : 0.0f;
+    const float gd_up = P.gout_d ? __ldg(P.gout_d) : P.gout_default;
+    const float ge_up = P.gout_e ? __ldg(P.gout_e) : P.gout_default;
+    if (M.skip_if_unit && gd_up == 1.0f && ge_up == 1.0f) return;
     const int r1 = cons_last_step(T);
     for (int r = cons_first_step(T); r <= r1; ++r) {
         cons_phase_A(P, T, S, r, tid, nt);
@@ -152,18 +155,24 @@ cons_scatter_kernel(const __grid_constant__ MultiCons M) {
 
 struct CtaStarts { int v[USL_MAX_SCALES + 1]; };
 
-__global__ void reduce_partials_kernel(const float* partials,
-                                       const CtaStarts starts_, int n_scales,
-                                       double* sums) {
-    const int* starts = starts_.v;
-    // one thread per (scale, term): fixed-order fp64 sum over that scale's CTAs
-    const int i = threadIdx.x;
-    if (i >= n_scales * NUM_ACC) return;
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* partials, const CtaStarts starts_,
+                       int n_scales, double* sums) {
+    // one block per (scale, term): fixed-order fp64 sum over that scale's rows
+    // (strided per-thread sums, then a fixed tree) -- deterministic
+    __shared__ double part[256];
+    const int i = blockIdx.x;
     const int s = i / NUM_ACC, k = i % NUM_ACC;
     double t = 0.0;
-    for (int c = starts[s]; c < starts[s + 1]; ++c)
+    for (int c = starts_.v[s] + threadIdx.x; c < starts_.v[s + 1]; c += 256)
         t += (double)partials[(long long)c * NUM_ACC + k];
-    sums[i] = t;
+    part[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[i] = part[0];
 }
 
 __global__ void combine_kernel(const double* sums, const float* coef,
@@ -274,6 +283,45 @@ static int plan(const UslLossConfig* cfgs, const UslLossScale* scales, int n,
 
 using namespace usl;
 
+static int fill_all(const UslLossConfig* cfgs, const UslLossScale* scales,
+                    int n, bool bwd, LossParams* P) {
+    if (n < 1 || n > USL_MAX_SCALES) return USL_ERR_ARG;
+    for (int i = 0; i < n; ++i) {
+        const int rc = fill_params(&cfgs[i], &scales[i], bwd, &P[i]);
+        if (rc != USL_OK) return rc;
+    }
+    return USL_OK;
+}
+
+extern "C" int usl_loss_plan(const UslLossConfig* cfgs,
+                             const UslLossScale* scales, int n_scales,
+                             int mode, int* cta_starts) {
+    if (!cfgs || !scales || !cta_starts) return USL_ERR_ARG;
+    if (mode != USL_MODE_FWD && mode != USL_MODE_GRAD) return USL_ERR_ARG;
+    if (march_eligible(cfgs, scales, n_scales)) {
+        MarchPlan M;
+        M.n = n_scales;
+        int rc = fill_all(cfgs, scales, n_scales, false, M.P);
+        if (rc != USL_OK) return rc;
+        rc = march_plan(&M, mode == USL_MODE_GRAD);
+        if (rc == USL_OK) {
+            // one row of partial sums per unit
+            cta_starts[0] = 0;
+            for (int i = 0; i < n_scales; ++i)
+                cta_starts[i + 1] = cta_starts[i] + M.units[i];
+            return USL_OK;
+        }
+        if (rc != USL_ERR_UNSUPPORTED) return rc;
+    }
+    if (mode == USL_MODE_GRAD) return USL_ERR_UNSUPPORTED;
+    MultiParams M;
+    size_t smem; int nt;
+    const int rc = plan(cfgs, scales, n_scales, false, &M, &smem, &nt);
+    if (rc != USL_OK) return rc;
+    for (int i = 0; i <= n_scales; ++i) cta_starts[i] = M.cta_start[i];
+    return USL_OK;
+}
+
 extern "C" int usl_loss_fwd_ctas(const UslLossScale* s) {
     if (!s || s->B <= 0 || s->h < 3 || s->w < 3) return USL_ERR_ARG;
     int TW, R;
@@ -281,13 +329,44 @@ extern "C" int usl_loss_fwd_ctas(const UslLossScale* s) {
     return ((s->w + TW - 1) / TW) * ((s->h + R - 1) / R) * s->B;
 }
 
+// The marching path, if every scale qualifies: 1 = launched, 0 = not eligible.
+static int try_march(const UslLossConfig* cfgs, const UslLossScale* scales,
+                     int n, bool grad, float* partials, const float* gout_d,
+                     const float* gout_e, int accumulate, int skip_if_unit,
+                     cudaStream_t st, int* rc_out) {
+    if (!march_eligible(cfgs, scales, n)) return 0;
+    MarchPlan M;
+    M.n = n;
+    int rc = fill_all(cfgs, scales, n, false, M.P);
+    if (rc != USL_OK) { *rc_out = rc; return 1; }
+    rc = march_plan(&M, grad);
+    if (rc == USL_ERR_UNSUPPORTED) return 0;
+    if (rc != USL_OK) { *rc_out = rc; return 1; }
+    long long row = 0;
+    for (int i = 0; i < n; ++i) {
+        LossParams& p = M.P[i];
+        p.partials = partials ? partials + row * NUM_ACC : nullptr;
+        row += M.units[i];
+        p.gout_d = gout_d; p.gout_e = gout_e;
+        p.grad_disp_accumulate =
+            (accumulate && (p.terms & (TERM_CONS_D | TERM_CONS_U))) ? 1 : 0;
+        if (grad && (!p.grad_disp || !p.grad_unc)) { *rc_out = USL_ERR_ARG; return 1; }
+    }
+    *rc_out = march_launch(&M, grad, skip_if_unit, st);
+    return 1;
+}
+
 extern "C" int usl_loss_fwd(const UslLossConfig* cfgs,
                             const UslLossScale* scales, int n_scales,
                             float* partials, void* stream) {
     if (!partials) return USL_ERR_ARG;
+    int rc = USL_OK;
+    if (try_march(cfgs, scales, n_scales, false, partials, nullptr, nullptr, 0,
+                  0, (cudaStream_t)stream, &rc))
+        return rc;
     MultiParams M;
     size_t smem; int nt;
-    const int rc = plan(cfgs, scales, n_scales, false, &M, &smem, &nt);
+    rc = plan(cfgs, scales, n_scales, false, &M, &smem, &nt);
     if (rc != USL_OK) return rc;
     for (int i = 0; i < n_scales; ++i)
         M.P[i].partials = partials + (long long)M.cta_start[i] * NUM_ACC;
@@ -307,7 +386,7 @@ extern "C" int usl_loss_reduce(const float* partials, const int* cta_starts,
         return USL_ERR_ARG;
     CtaStarts st;
     for (int i = 0; i <= n_scales; ++i) st.v[i] = cta_starts[i];
-    reduce_partials_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(
+    reduce_partials_kernel<<<n_scales * NUM_ACC, 256, 0, (cudaStream_t)stream>>>(
         partials, st, n_scales, sums);
     return check_launch();
 }
@@ -322,31 +401,25 @@ extern "C" int usl_loss_combine(const double* sums, const float* coef,
     return check_launch();
 }
 
-extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
-                            const UslLossScale* scales, int n_scales,
-                            const float* gout_disp, const float* gout_err,
-                            int stages, void* stream) {
-    if (!(stages & (USL_BWD_STAGE_SCATTER | USL_BWD_STAGE_MAIN)))
-        return USL_ERR_ARG;
-    MultiParams M;
-    size_t smem; int nt;
-    int rc = plan(cfgs, scales, n_scales, true, &M, &smem, &nt);
-    if (rc != USL_OK) return rc;
-    // 1) transposed warp of the consistency terms -> grad_disp (pure store)
+// The deterministic transposed warp of the consistency terms -> grad_disp
+// (pure store).  Returns the number of scales that scatter.
+static int launch_scatter(const LossParams* P, int n_scales,
+                          const float* gout_disp, const float* gout_err,
+                          float gout_default, int skip_if_unit, bool launch,
+                          cudaStream_t st, int* rc_out) {
     MultiCons C;
-    C.n = 0; C.cta_start[0] = 0;
+    C.n = 0; C.cta_start[0] = 0; C.skip_if_unit = skip_if_unit;
     size_t csmem = 0;
     for (int i = 0; i < n_scales; ++i) {
-        LossParams& p = M.P[i];
-        p.gout_d = gout_disp; p.gout_e = gout_err;
-        p.grad_disp_accumulate = 0;
+        const LossParams& p = P[i];
         if (!(p.terms & (TERM_CONS_D | TERM_CONS_U))) continue;
-        if (!p.grad_disp) return USL_ERR_ARG;
+        if (!p.grad_disp) { *rc_out = USL_ERR_ARG; return 0; }
         ConsParams c = {};
         c.B = p.B; c.h = p.h; c.w = p.w;
         c.disp = p.disp; c.d_bs = p.d_bs; c.d_cs = p.d_cs;
         c.unc = p.unc; c.u_bs = p.u_bs; c.u_cs = p.u_cs;
         c.gout_d = gout_disp; c.gout_e = gout_err;
+        c.gout_default = gout_default;
         c.grad_disp = p.grad_disp; c.gd_bs = p.gd_bs; c.gd_cs = p.gd_cs;
         c.terms = p.terms & (TERM_CONS_D | TERM_CONS_U);
         c.coef_dd = p.coef[ACC_CONS_D]; c.coef_ud = p.coef[ACC_CONS_U];
@@ -358,17 +431,77 @@ extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
         C.cta_start[k + 1] = C.cta_start[k] + C.strips[k] * c.B;
         const size_t bytes = cons_ring_floats(c.w) * sizeof(float);
         if (bytes > csmem) csmem = bytes;
-        p.grad_disp_accumulate = 1;
     }
-    if (C.n > 0 && (stages & USL_BWD_STAGE_SCATTER)) {
-        if (csmem > 227 * 1024) return USL_ERR_UNSUPPORTED;
+    *rc_out = USL_OK;
+    if (C.n > 0 && launch) {
+        if (csmem > 227 * 1024) { *rc_out = USL_ERR_UNSUPPORTED; return C.n; }
         if (cudaFuncSetAttribute(cons_scatter_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)csmem) != cudaSuccess)
-            return USL_ERR_CUDA;
-        cons_scatter_kernel<<<C.cta_start[C.n], 256, csmem,
-                              (cudaStream_t)stream>>>(C);
-        rc = check_launch();
+                                 (int)csmem) != cudaSuccess) {
+            *rc_out = USL_ERR_CUDA; return C.n;
+        }
+        cons_scatter_kernel<<<C.cta_start[C.n], 256, csmem, st>>>(C);
+        *rc_out = check_launch();
+    }
+    return C.n;
+}
+
+extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
+                             const UslLossScale* scales, int n_scales,
+                             const float* gout_disp, const float* gout_err,
+                             float* partials, int flags, void* stream) {
+    if (!march_eligible(cfgs, scales, n_scales)) return USL_ERR_UNSUPPORTED;
+    LossParams P[USL_MAX_SCALES];
+    int rc = fill_all(cfgs, scales, n_scales, false, P);
+    if (rc != USL_OK) return rc;
+    const int skip = (flags & USL_GRAD_SKIP_IF_UNIT) ? 1 : 0;
+    launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
+                   (cudaStream_t)stream, &rc);
+    if (rc != USL_OK) return rc;
+    if (!try_march(cfgs, scales, n_scales, true, partials, gout_disp, gout_err,
+                   1, skip, (cudaStream_t)stream, &rc))
+        return USL_ERR_UNSUPPORTED;
+    return rc;
+}
+
+extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
+                            const UslLossScale* scales, int n_scales,
+                            const float* gout_disp, const float* gout_err,
+                            int stages, void* stream) {
+    if (!(stages & (USL_BWD_STAGE_SCATTER | USL_BWD_STAGE_MAIN)))
+        return USL_ERR_ARG;
+    int rc = USL_OK;
+    if (march_eligible(cfgs, scales, n_scales)) {
+        // a NULL upstream gradient means "this output takes no part": 0
+        LossParams P[USL_MAX_SCALES];
+        rc = fill_all(cfgs, scales, n_scales, false, P);
+        if (rc != USL_OK) return rc;
+        launch_scatter(P, n_scales, gout_disp, gout_err, 0.0f, 0,
+                       (stages & USL_BWD_STAGE_SCATTER) != 0,
+                       (cudaStream_t)stream, &rc);
+        if (rc != USL_OK) return rc;
+        if (!(stages & USL_BWD_STAGE_MAIN)) return USL_OK;
+        if (gout_disp && gout_err &&
+            try_march(cfgs, scales, n_scales, true, nullptr, gout_disp,
+                      gout_err, 1, 0, (cudaStream_t)stream, &rc))
+            return rc;
+        // (an absent upstream gradient is rare: fall through to the general
+        //  kernel, which treats NULL as zero)
+        stages &= ~USL_BWD_STAGE_SCATTER;
+    }
+    MultiParams M;
+    size_t smem; int nt;
+    rc = plan(cfgs, scales, n_scales, true, &M, &smem, &nt);
+    if (rc != USL_OK) return rc;
+    for (int i = 0; i < n_scales; ++i) {
+        LossParams& p = M.P[i];
+        p.gout_d = gout_disp; p.gout_e = gout_err;
+        p.grad_disp_accumulate =
+            (p.terms & (TERM_CONS_D | TERM_CONS_U)) ? 1 : 0;
+    }
+    if (stages & USL_BWD_STAGE_SCATTER) {
+        launch_scatter(M.P, n_scales, gout_disp, gout_err, 0.0f, 0, true,
+                       (cudaStream_t)stream, &rc);
         if (rc != USL_OK) return rc;
     }
     // 2) everything else, adding to the scattered part

@@ -148,25 +148,38 @@ def _array(cls, items):
 # --------------------------------------------------------------------------
 # launches
 # --------------------------------------------------------------------------
+MODE_FWD, MODE_GRAD = 0, 1
+GRAD_SKIP_IF_UNIT = 1
+
+
+def plan_rows(cfg_arr, sc_arr, n: int, mode: int) -> Optional[List[int]]:
+    """Row offsets of every scale in the partial-sum buffer for a launch in
+    `mode`; None if the one-pass sums+gradient launch does not apply."""
+    starts = (C.c_int * (n + 1))()
+    rc = lib().usl_loss_plan(cfg_arr, sc_arr, n, mode, starts)
+    if rc == _lib.USL_ERR_UNSUPPORTED and mode == MODE_GRAD:
+        return None
+    check(rc, 'usl_loss_plan')
+    return list(starts)
+
+
 def loss_forward(cfgs: Sequence[UslLossConfig],
                  scales: Sequence[UslLossScale], device,
-                 reduce_group=None) -> Tuple[Tensor, Tensor, Tensor]:
-    """One fused forward launch over all scales.
+                 reduce_group=None, with_grad: bool = False
+                 ) -> Tuple[Tensor, Tensor, Tensor]:
+    """One fused launch over all scales.
 
     Returns (disp_loss, error_loss, sums): two 0-dim fp32 tensors and the
     fp64[n_scales, 6] raw per-term sums (all-reduced over `reduce_group` when
-    the batch is sharded over ranks)."""
+    the batch is sharded over ranks).
+
+    with_grad: use the one-pass launch that also writes the gradients (for
+    unit upstream gradients) into the grad_* buffers of `scales`; the caller
+    has checked with `plan_rows(..., MODE_GRAD)` that it applies."""
     L = lib()
     n = len(scales)
-    counts = []
-    for s in scales:
-        c = L.usl_loss_fwd_ctas(C.byref(s))
-        if c < 0:
-            check(c, 'usl_loss_fwd_ctas')
-        counts.append(c)
-    starts = [0]
-    for c in counts:
-        starts.append(starts[-1] + c)
+    cfg_arr, sc_arr = _array(UslLossConfig, cfgs), _array(UslLossScale, scales)
+    starts = plan_rows(cfg_arr, sc_arr, n, MODE_GRAD if with_grad else MODE_FWD)
     partials = torch.empty(starts[-1] * USL_NUM_TERMS, dtype=torch.float32,
                            device=device)
     sums = torch.empty(n, USL_NUM_TERMS, dtype=torch.float64, device=device)
@@ -174,9 +187,12 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
     out_err = torch.empty((), dtype=torch.float32, device=device)
     coef = coef_tensor(tuple(tuple(c.coef) for c in cfgs), device)
     stream = _stream(partials)
-    cfg_arr, sc_arr = _array(UslLossConfig, cfgs), _array(UslLossScale, scales)
-    check(L.usl_loss_fwd(cfg_arr, sc_arr, n, partials.data_ptr(), stream),
-          'usl_loss_fwd')
+    if with_grad:
+        check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None,
+                              partials.data_ptr(), 0, stream), 'usl_loss_grad')
+    else:
+        check(L.usl_loss_fwd(cfg_arr, sc_arr, n, partials.data_ptr(), stream),
+              'usl_loss_fwd')
     check(L.usl_loss_reduce(partials.data_ptr(), (C.c_int * (n + 1))(*starts),
                             n, sums.data_ptr(), stream), 'usl_loss_reduce')
     if reduce_group is not None:
@@ -212,6 +228,19 @@ def loss_backward(cfgs: Sequence[UslLossConfig],
                          _array(UslLossScale, scales), len(scales),
                          _ptr(g_disp), _ptr(g_err), stages, stream),
           'usl_loss_bwd')
+
+
+def loss_regrad(cfgs: Sequence[UslLossConfig], scales: Sequence[UslLossScale],
+                g_disp: Tensor, g_err: Tensor, device) -> None:
+    """Backward half of the one-pass scheme: the gradients written by the
+    forward are exact for unit upstream gradients; this launch recomputes them
+    for any other upstream pair and returns at once (on the device -- no host
+    synchronisation) when both are 1."""
+    stream = torch.cuda.current_stream(device).cuda_stream
+    check(lib().usl_loss_grad(_array(UslLossConfig, cfgs),
+                              _array(UslLossScale, scales), len(scales),
+                              g_disp.data_ptr(), g_err.data_ptr(), None,
+                              GRAD_SKIP_IF_UNIT, stream), 'usl_loss_grad')
 
 
 def pyramid(x: Tensor, scales: int) -> List[Tensor]:
@@ -391,46 +420,8 @@ class FusedLoss(torch.autograd.Function):
     (loss.py:418 detaches the error)."""
 
     @staticmethod
-    def forward(ctx, settings: LossSettings, specs: Sequence[ScaleSpec],
-                group, *tensors: Tensor):
-        for i, t in enumerate(tensors):
-            require_cuda_f32(t, f'tensor {i}')
-        tensors = tuple(planes(t) for t in tensors)
-        device = tensors[0].device
-        cfgs, scales, errs = [], [], []
-        for sp in specs:
-            b, h, w = _spec_shape(sp, tensors)
-            err_out = None
-            if sp.want_err:
-                err_out = torch.empty(b, 2, h, w, dtype=torch.float32,
-                                      device=device)
-                errs.append(err_out)
-            cfgs.append(make_config(sp.terms, settings, sp.coefs))
-            scales.append(make_scale(
-                tensors[sp.images] if sp.images >= 0 else None,
-                _pair(tensors[sp.disp], sp.disp_ch) if sp.disp >= 0 else None,
-                _pair(tensors[sp.unc], sp.unc_ch) if sp.unc >= 0 else None,
-                shape=(b, h, w),
-                recon_in=tensors[sp.recon] if sp.recon >= 0 else None,
-                err_in=tensors[sp.err] if sp.err >= 0 else None,
-                err_out=err_out))
-        out_disp, out_err, sums = loss_forward(cfgs, scales, device, group)
-        ctx.settings, ctx.specs = settings, specs
-        ctx.save_for_backward(*tensors)
-        ctx.mark_non_differentiable(sums, *errs)
-        ctx.set_materialize_grads(False)
-        return (out_disp, out_err, sums) + tuple(errs)
-
-    @staticmethod
-    def backward(ctx, g_disp, g_err, *unused):
-        tensors = ctx.saved_tensors
-        specs, settings = ctx.specs, ctx.settings
-        device = tensors[0].device
-        if g_disp is not None:
-            g_disp = g_disp.contiguous()
-        if g_err is not None:
-            g_err = g_err.contiguous()
-        # which channels of each tensor the kernels will fully overwrite
+    def _grad_buffers(specs, tensors):
+        """Fresh gradient tensors for every tensor the kernels write into."""
         covered = [set() for _ in tensors]
         for sp in specs:
             if sp.disp >= 0:
@@ -446,9 +437,19 @@ class FusedLoss(torch.autograd.Function):
             alloc = torch.empty_like if len(covered[i]) == t.size(1) \
                 else torch.zeros_like
             grads[i] = alloc(t, memory_format=torch.contiguous_format)
+        return grads
+
+    @staticmethod
+    def _build(settings, specs, tensors, device, grads=None, errs=None):
         cfgs, scales = [], []
         for sp in specs:
             b, h, w = _spec_shape(sp, tensors)
+            err_out = None
+            if errs is not None and sp.want_err:
+                err_out = torch.empty(b, 2, h, w, dtype=torch.float32,
+                                      device=device)
+                errs.append(err_out)
+            g = grads if grads is not None else [None] * len(tensors)
             cfgs.append(make_config(sp.terms, settings, sp.coefs))
             scales.append(make_scale(
                 tensors[sp.images] if sp.images >= 0 else None,
@@ -457,13 +458,75 @@ class FusedLoss(torch.autograd.Function):
                 shape=(b, h, w),
                 recon_in=tensors[sp.recon] if sp.recon >= 0 else None,
                 err_in=tensors[sp.err] if sp.err >= 0 else None,
-                grad_disp=_pair(grads[sp.disp], sp.disp_ch)
-                if sp.disp >= 0 else None,
-                grad_unc=_pair(grads[sp.unc], sp.unc_ch)
-                if sp.unc >= 0 else None,
-                grad_recon_out=grads[sp.recon] if sp.recon >= 0 else None))
-        loss_backward(cfgs, scales, g_disp, g_err, device)
+                err_out=err_out,
+                grad_disp=_pair(g[sp.disp], sp.disp_ch)
+                if sp.disp >= 0 and g[sp.disp] is not None else None,
+                grad_unc=_pair(g[sp.unc], sp.unc_ch)
+                if sp.unc >= 0 and g[sp.unc] is not None else None,
+                grad_recon_out=g[sp.recon] if sp.recon >= 0 else None))
+        return cfgs, scales
+
+    @staticmethod
+    def forward(ctx, settings: LossSettings, specs: Sequence[ScaleSpec],
+                group, *tensors: Tensor):
+        for i, t in enumerate(tensors):
+            require_cuda_f32(t, f'tensor {i}')
+        tensors = tuple(planes(t) for t in tensors)
+        device = tensors[0].device
+        ctx.settings, ctx.specs = settings, specs
+        ctx.onepass = None
+        errs: List[Tensor] = []
+        if any(ctx.needs_input_grad[3:]):
+            # one pass: the sums and (for unit upstream gradients) the
+            # gradients together -- see usl_loss_grad in include/usl.h
+            grads = FusedLoss._grad_buffers(specs, tensors)
+            cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
+                                            grads, errs)
+            n = len(scales)
+            if plan_rows(_array(UslLossConfig, cfgs),
+                         _array(UslLossScale, scales), n,
+                         MODE_GRAD) is not None:
+                out_disp, out_err, sums = loss_forward(cfgs, scales, device,
+                                                       group, with_grad=True)
+                ctx.onepass = grads
+                ctx.save_for_backward(*tensors)
+                ctx.mark_non_differentiable(sums, *errs)
+                ctx.set_materialize_grads(False)
+                return (out_disp, out_err, sums) + tuple(errs)
+            errs = []
+        cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
+                                        None, errs)
+        out_disp, out_err, sums = loss_forward(cfgs, scales, device, group)
+        ctx.save_for_backward(*tensors)
+        ctx.mark_non_differentiable(sums, *errs)
+        ctx.set_materialize_grads(False)
+        return (out_disp, out_err, sums) + tuple(errs)
+
+    @staticmethod
+    def backward(ctx, g_disp, g_err, *unused):
+        tensors = ctx.saved_tensors
+        specs, settings = ctx.specs, ctx.settings
+        device = tensors[0].device
+        if g_disp is not None:
+            g_disp = g_disp.contiguous()
+        if g_err is not None:
+            g_err = g_err.contiguous()
         needs = ctx.needs_input_grad[3:]
+        if ctx.onepass is not None:
+            grads = ctx.onepass
+            zero = None
+            if g_disp is None or g_err is None:
+                zero = torch.zeros((), dtype=torch.float32, device=device)
+            cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
+                                            grads)
+            loss_regrad(cfgs, scales, zero if g_disp is None else g_disp,
+                        zero if g_err is None else g_err, device)
+            return (None, None, None) + tuple(
+                g if need else None for g, need in zip(grads, needs))
+        grads = FusedLoss._grad_buffers(specs, tensors)
+        cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
+                                        grads)
+        loss_backward(cfgs, scales, g_disp, g_err, device)
         return (None, None, None) + tuple(
             g if need else None for g, need in zip(grads, needs))
 
