@@ -16,6 +16,8 @@ SRC = os.path.join(HERE, 'emu', 'emu.cpp')
 OUT = os.path.join(HERE, 'emu', 'build', 'libemu.so')
 SRC_MARCH = os.path.join(HERE, 'emu', 'emu_march.cpp')
 OUT_MARCH = os.path.join(HERE, 'emu', 'build', 'libemu_march.so')
+SRC_COL = os.path.join(HERE, 'emu', 'emu_col.cpp')
+OUT_COL = os.path.join(HERE, 'emu', 'build', 'libemu_col.so')
 CSRC = os.path.join(os.path.dirname(HERE), 'uncertainty_model_b200', 'csrc')
 
 _emu = None
@@ -143,5 +145,67 @@ def emu_march_scale(settings: LossSettings, terms, coefs, images, pred, *,
     sums_g = (C.c_double * 6)()
     assert L.emu_march_grad(C.byref(cfg), C.byref(sc), TW, R, acc, gout,
                             sums_g) == 0
+    return dict(sums=list(sums), sums_grad=list(sums_g), err=err_out,
+                recon=recon_out, grad_pred=grad_pred)
+
+
+_emu_col = None
+
+
+def emu_col():
+    global _emu_col
+    if _emu_col is None:
+        deps = [SRC_COL] + [os.path.join(CSRC, f) for f in
+                            ('col_core.cuh', 'loss_core.cuh', 'usl_math.cuh')]
+        if not os.path.exists(OUT_COL) or any(
+                os.path.getmtime(d) > os.path.getmtime(OUT_COL) for d in deps):
+            os.makedirs(os.path.dirname(OUT_COL), exist_ok=True)
+            subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC',
+                            '-ffp-contract=off', '-x', 'c++', SRC_COL, '-o',
+                            OUT_COL], check=True)
+        lib = C.CDLL(OUT_COL)
+        lib.emu_col_fwd.restype = C.c_int
+        lib.emu_col_fwd.argtypes = [C.POINTER(UslLossConfig),
+                                    C.POINTER(UslLossScale), C.c_int, C.c_int,
+                                    C.POINTER(C.c_double)]
+        lib.emu_col_grad.restype = C.c_int
+        lib.emu_col_grad.argtypes = [C.POINTER(UslLossConfig),
+                                     C.POINTER(UslLossScale), C.c_int, C.c_int,
+                                     C.c_int, C.POINTER(C.c_float),
+                                     C.POINTER(C.c_double)]
+        _emu_col = lib
+    return _emu_col
+
+
+def emu_col_scale(settings: LossSettings, terms, coefs, images, pred, *,
+                  g=(1.0, 1.0), maxT=512, R=16, consR=16, want_recon=False,
+                  grad_recon_in=None):
+    """The column-marching kernels (forward-only mode, then the one-pass
+    sums+gradient mode on top of the emulated scatter) for ONE scale.
+
+    Returns dict(sums, sums_grad, err, recon, grad_pred)."""
+    L = emu_col()
+    b, _, h, w = pred.shape
+    images = images.contiguous()
+    pred = pred.contiguous()
+    cfg = make_config(terms, settings, coefs)
+    err_out = torch.full((b, 2, h, w), float('nan'))
+    recon_out = torch.full((b, 6, h, w), float('nan')) if want_recon else None
+    sc = make_scale(images, pred[:, 0:2], pred[:, 2:4], shape=(b, h, w),
+                    err_out=err_out, recon_out=recon_out)
+    sums = (C.c_double * 6)()
+    assert L.emu_col_fwd(C.byref(cfg), C.byref(sc), maxT, R, sums) == 0
+    grad_pred = torch.full((b, 4, h, w), float('nan'))
+    sc = make_scale(images, pred[:, 0:2], pred[:, 2:4], shape=(b, h, w),
+                    grad_recon_in=grad_recon_in, grad_disp=grad_pred[:, 0:2],
+                    grad_unc=grad_pred[:, 2:4])
+    gout = (C.c_float * 2)(*g)
+    acc = 0
+    if terms & 34:          # TERM_CONS_D | TERM_CONS_U
+        emu().emu_cons_scatter(C.byref(cfg), C.byref(sc), consR, gout)
+        acc = 1
+    sums_g = (C.c_double * 6)()
+    assert L.emu_col_grad(C.byref(cfg), C.byref(sc), maxT, R, acc, gout,
+                          sums_g) == 0
     return dict(sums=list(sums), sums_grad=list(sums_g), err=err_out,
                 recon=recon_out, grad_pred=grad_pred)

@@ -1,0 +1,677 @@
+// Column-marching form of the fused loss kernels (forward + one-pass gradient):
+// the hot path of the training step.  Same mathematics as loss_core.cuh (see
+// its header for the reference citations: utils.py:65-135, loss.py:43-151,
+// 167-188,208-264,389-434,539-568), organised around what bounds it on B200.
+//
+// The path is NOT HBM bound: a pixel of one view costs ~500 issued instructions
+// (warp, 3x3 SSIM of three channels forward and backward, two consistency
+// warps, smoothness, uncertainty term) against 56 bytes of compulsory traffic,
+// and it needs ~120 floats of on-chip state per column (two rows of window-sum
+// history forward, two backward, the rows in flight).  Registers + shared
+// memory of one SM hold ~512 columns of state, so:
+//
+//  * one THREAD owns ONE column of ONE view for a whole row strip and marches
+//    down it, one image row per step; 512 threads (16 warps) per SM;
+//  * everything vertical lives in registers: the separable 3x3 window sums keep
+//    the horizontal 3-sums of the two previous rows (forward: {x, y, x^2+y^2,
+//    xy} per channel; backward: the three dSSIM maps per channel);
+//  * everything horizontal goes through single shared-memory rows (right
+//    neighbours of the reconstruction, left neighbours of the dSSIM maps),
+//    conflict free.  All rows of the CTA share ONE compile-time row stride and
+//    a thread sits at the same position in each of them, so every access is
+//    [thread base + immediate];
+//  * the opposite view's vertically blended row V(r) -- {R,G,B,disparity} as one
+//    16-byte element per column, zero padded -- is the only gathered input;
+//    coordinates are clamped into the padding instead of being range tested;
+//  * the unit of work -- one CTA -- is (sample, row strip, view set, column
+//    tile): a full-width row of one view (w = 512), of both views (w <= 256), or
+//    a column tile with a 2-column halo on each side (w > 512).  Every pyramid
+//    scale is its own launch (its own block size and row stride), so the
+//    geometry and the configuration are CTA-uniform kernel parameters;
+//
+// Step r of a strip [ya, yb)  (row r enters; results trail by two rows):
+//   P1  warp of row r from V(r): recon y(r), d(recon)/d(shift), |x - y| and its
+//       gradient; both consistency terms; vertical smoothness edge (r-1, r)
+//   -- barrier --
+//   P2  horizontal smoothness edge (c, c+1); horizontal 3-sums of row r; SSIM of
+//       window row q = r-2 -> dssim(q) and the maps
+//       G(q) = dSSIM/d{mean_y, E[y^2], E[xy]}
+//   -- barrier --
+//   P3  3x3 box of G -> d(loss)/d(recon) of row r-2, through the warp; error
+//       map row r-2 (up-sampled dssim + L1) -> reprojection and uncertainty
+//       terms; gradient row r-2 written; V(r+1) produced
+//   -- barrier --
+//
+// Every function is host+device: tests/emu runs the phases on the CPU with one
+// CState per emulated thread (same rings, same step order).
+#pragma once
+
+#include <stdint.h>
+#include <string.h>
+
+#include "loss_core.cuh"
+
+namespace usl {
+namespace ck {
+
+#if defined(__CUDA_ARCH__)
+USL_HD unsigned f2u(float f) { return __float_as_uint(f); }
+USL_HD float u2f(unsigned u) { return __uint_as_float(u); }
+USL_HD float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+USL_HD float fast_exp2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+USL_HD float fast_log2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+USL_HD F4 ld_f4(const F4* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    F4 r; r.x = t.x; r.y = t.y; r.z = t.z; r.w = t.w;
+    return r;
+}
+USL_HD void st_f4(F4* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+#else
+USL_HD unsigned f2u(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+USL_HD float u2f(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+USL_HD float fast_rcp(float x) { return 1.0f / x; }
+USL_HD float fast_exp2(float x) { return exp2f(x); }
+USL_HD float fast_log2(float x) { return log2f(x); }
+USL_HD F4 ld_f4(const F4* p) { return *p; }
+USL_HD void st_f4(F4* p, float a, float b, float c, float d) {
+    p->x = a; p->y = b; p->z = c; p->w = d;
+}
+#endif
+
+// s * sgn(v)   (torch: d|v|/dv = sign(v), 0 at 0): sign-bit transfer + zero test
+USL_HD float sgn_mul(float v, float s) {
+    const float r = u2f(f2u(s) ^ (f2u(v) & 0x80000000u));
+    return v == 0.0f ? 0.0f : r;
+}
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int VPAD = 2;         // zero columns on each side of a V row
+
+// ---- shared-memory layout -----------------------------------------------------
+// One arena per CTA: `SROW` floats per row (compile time); a view's segment of
+// a row is [2 pad | LW columns | 2 pad], the two views side by side.  A thread
+// sits at the same position `sb` in every row, so each access is [sb + imm].
+constexpr int SEG_PAD = 2;
+constexpr int NHIST_GRAD = 11;  // dI[3], y*dI[3], x*dI[3], l1, u
+constexpr int NHIST_FWD = 2;    // l1, u
+enum {
+    ROW_Y = 0,      // [3]  recon of the current row        (right neighbours read)
+    ROW_X = 3,      // [3]  own image row                   (right neighbours read)
+    ROW_DU = 6,     // [2]  own disparity, uncertainty      (right neighbour reads)
+    ROW_DS = 8,     // [4]  ring of channel-summed dssim rows
+    ROW_HS = 12,    // [3][NH] thread-private history of the rows in flight
+};
+USL_HD constexpr int row_gx(bool grad) {     // [9] G(q) of the current window row
+    return ROW_HS + 3 * (grad ? NHIST_GRAD : NHIST_FWD);
+}
+USL_HD constexpr int row_ed(bool grad) { return row_gx(grad) + 9; }   // [2]
+USL_HD constexpr int n_rows(bool grad) { return grad ? row_ed(true) + 2 : row_gx(false); }
+
+struct CGeo {                // per-CTA constants
+    int b;                   // sample
+    int v0, nv;              // first view, number of views (1 or 2)
+    int xa, xb;              // owned columns
+    int cbeg, LW;            // first column incl. halo; columns incl. halo
+    int ya, yb;              // owned rows
+    int qlo;                 // first window row this strip forms
+    float sH, sW;            // (h-2 -> h), (w-2 -> w) align-corners scales
+    float gd_up, ge_up;      // upstream gradients (GRAD)
+};
+
+// per-step tables (one entry per row of the strip), see c_init_unit
+struct alignas(16) RowT {
+    float tyw;               // transposed up-sample row weight of q = r - 2
+    float ay_w1;             // up-sample (h-2 -> h) weight of tap i1, y = r - 2
+    int ay_o0, ay_o1;        // float offsets (from sb) of the dssim ring rows i0, i1
+};
+struct alignas(16) RowV {    // vertical taps of the warp for row r
+    int i0, i1;              // source rows (clamped into the image)
+    float w0, w1;            // weights (zero for rows outside the image)
+};
+
+struct CRings {
+    float* rows;    // [n_rows][SROW]
+    F4* V;          // [nv][w + 2*VPAD]
+    RowT* RT;       // [R + 6]
+    RowV* RV;       // [R + 6]
+};
+
+USL_HD int c_first_row(const CGeo& G) { return G.ya - 2; }
+USL_HD int c_last_row(const CGeo& G) { return G.yb + 1; }
+
+// floats of shared memory for one CTA
+USL_HD size_t c_floats(int srow, int w, int nv, int R, bool grad) {
+    size_t n = (size_t)n_rows(grad) * srow;
+    n += (size_t)nv * (w + 2 * VPAD) * 4;
+    n += (size_t)(R + 6) * 8;
+    return (n + 3) & ~(size_t)3;
+}
+
+USL_HD CRings c_carve(float* base, int srow, int w, int nv, int R, bool grad) {
+    CRings S;
+    S.V = reinterpret_cast<F4*>(base); base += (size_t)nv * (w + 2 * VPAD) * 4;
+    S.RT = reinterpret_cast<RowT*>(base); base += (size_t)(R + 6) * 4;
+    S.RV = reinterpret_cast<RowV*>(base); base += (size_t)(R + 6) * 4;
+    S.rows = base;
+    return S;
+}
+
+struct CState {
+    float x[3], d, u;        // own inputs, row r
+    float xp[3], dp, up;     // row r-1
+    float xn[3], dn, un;     // row r+1 (in flight)
+    float y[3];              // recon of row r                    (P1 -> P2)
+    float H[2][3][4];        // horizontal 3-sums of the two previous rows
+    float HG[2][3][3];       // ... of G of the two previous window rows
+    float gd[3], gu[3];      // gradient accumulators of rows r, r-1, r-2
+    float acc[NUM_ACC];
+    // per-thread constants
+    float xbase;             // linspace(0,1,w) at c
+    float txw;               // transposed up-sample column weight (GRAD)
+    float axw;               // up-sample column weight of tap i1
+    float own;               // 1 where the column belongs to the unit
+    float sign;              // -1 left view, +1 right view
+    float* sb;               // the thread's position in row 0 of the arena
+    const F4* vrow0;         // column 0 of the own view's V row
+    int ax0, ax1;            // column offsets (from the own column) of the up-sample taps
+    unsigned o_img, o_d, o_u;   // element offsets of (b, own view, row 0, c)
+    unsigned o_oi, o_od;        // ... of (b, opposite view, row 0, c): img, disp
+    unsigned o_gd, o_gu;        // ... in the gradient tensors
+    int v, vi, c, lc;
+    bool active, win_ok, has1;
+};
+
+USL_HD float c_warp_coord(float xbase, float shift, float half_n) {
+    const float x = xbase + shift;
+    const float g = fmaf(2.0f, x, -1.0f);
+    return fmaf(g + 1.0f, half_n, -0.5f);
+}
+
+// ---- CTA prologue -----------------------------------------------------------
+template <bool GRAD>
+USL_HD void c_thread_init(const LossParams& P, const CGeo& G, const CRings& S,
+                          int tid, CState& T) {
+    const int w = P.w;
+    T.vi = tid / G.LW;
+    T.lc = tid - T.vi * G.LW;
+    T.active = tid < G.nv * G.LW;
+    if (!T.active) { T.vi = 0; T.lc = 0; }
+    T.v = G.v0 + T.vi;
+    T.c = G.cbeg + T.lc;
+    T.sign = T.v ? 1.0f : -1.0f;
+    for (int a = 0; a < 2; ++a)
+        for (int c = 0; c < 3; ++c) {
+            for (int q = 0; q < 4; ++q) T.H[a][c][q] = 0.f;
+            for (int m = 0; m < 3; ++m) T.HG[a][c][m] = 0.f;
+        }
+    for (int a = 0; a < 3; ++a) T.gd[a] = T.gu[a] = 0.f;
+    for (int k = 0; k < NUM_ACC; ++k) T.acc[k] = 0.f;
+    for (int c = 0; c < 3; ++c) T.x[c] = T.xp[c] = T.xn[c] = T.y[c] = 0.f;
+    T.d = T.dp = T.dn = 0.f;
+    T.u = T.up = T.un = 1.f;
+    T.xbase = linspace01(T.c, w);
+    T.own = (T.active && T.c >= G.xa && T.c < G.xb) ? 1.f : 0.f;
+    T.win_ok = T.c <= w - 3;
+    T.has1 = T.c + 1 < w;
+    T.sb = S.rows + T.vi * (G.LW + 2 * SEG_PAD) + SEG_PAD + T.lc;
+    T.vrow0 = S.V + T.vi * (w + 2 * VPAD) + VPAD;
+    T.o_img = (unsigned)((long long)G.b * P.img_bs + (long long)T.v * 3 * P.img_cs + T.c);
+    T.o_oi = (unsigned)((long long)G.b * P.img_bs + (long long)(1 - T.v) * 3 * P.img_cs + T.c);
+    T.o_d = (unsigned)((long long)G.b * P.d_bs + (long long)T.v * P.d_cs + T.c);
+    T.o_od = (unsigned)((long long)G.b * P.d_bs + (long long)(1 - T.v) * P.d_cs + T.c);
+    T.o_u = (unsigned)((long long)G.b * P.u_bs + (long long)T.v * P.u_cs + T.c);
+    T.o_gd = (unsigned)((long long)G.b * P.gd_bs + (long long)T.v * P.gd_cs + T.c);
+    T.o_gu = (unsigned)((long long)G.b * P.gu_bs + (long long)T.v * P.gu_cs + T.c);
+    T.txw = 0.f; T.axw = 0.f; T.ax0 = T.ax1 = 0;
+    if (!T.active) return;
+    const TapAC ax = ac_taps(T.c, G.sW, w - 2);
+    // a zero-weight tap may lie outside what the unit forms: point it at i0
+    const int i1 = ax.w1 != 0.f ? ax.i1 : ax.i0;
+    T.ax0 = ax.i0 - T.c;
+    T.ax1 = i1 - T.c;
+    T.axw = ax.w1;
+    if (GRAD && T.c <= w - 3)
+        T.txw = upsample_transpose_weight(T.c, w - 2, w, G.sW);
+}
+
+// Zeroes the exchange rows (the pads must be zero, the rest is overwritten
+// before it is read) and the V pads; fills the per-row tables.
+template <int SROW, bool GRAD>
+USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
+                        int tid, int nt) {
+    const int R = P.R;
+    for (int i = tid; i < R + 6; i += nt) {
+        const int r = G.ya - 2 + i;         // step
+        const int y = r - 2;                // row finalised / window row
+        RowT t;
+        t.tyw = (GRAD && y >= 0 && y <= P.h - 3)
+                    ? upsample_transpose_weight(y, P.h - 2, P.h, G.sH) : 0.0f;
+        t.ay_w1 = 0.f; t.ay_o0 = t.ay_o1 = ROW_DS * SROW;
+        if (y >= 0 && y < P.h) {
+            const TapAC ay = ac_taps(y, G.sH, P.h - 2);
+            const int i1 = ay.w1 != 0.f ? ay.i1 : ay.i0;
+            t.ay_w1 = ay.w1;
+            t.ay_o0 = (ROW_DS + (ay.i0 & 3)) * SROW;
+            t.ay_o1 = (ROW_DS + (i1 & 3)) * SROW;
+        }
+        S.RT[i] = t;
+        RowV v;
+        v.i0 = v.i1 = 0; v.w0 = v.w1 = 0.f;
+        if (r >= 0 && r < P.h) {
+            const Tap2 ty = warp_row_taps(r, P.h);
+            const bool ok0 = ty.i0 >= 0 && ty.i0 < P.h;
+            const bool ok1 = ty.i0 + 1 >= 0 && ty.i0 + 1 < P.h;
+            v.w0 = ok0 ? ty.w0 : 0.0f;
+            v.w1 = ok1 ? ty.w1 : 0.0f;
+            v.i0 = ok0 ? ty.i0 : ty.i0 + 1;
+            v.i1 = ok1 ? ty.i0 + 1 : ty.i0;
+        }
+        S.RV[i] = v;
+    }
+    for (int i = tid; i < G.nv * 2 * VPAD; i += nt) {
+        const int vi = i / (2 * VPAD), k = i - vi * 2 * VPAD;
+        const int col = k < VPAD ? k : P.w + k;
+        st_f4(S.V + (size_t)vi * (P.w + 2 * VPAD) + col, 0.f, 0.f, 0.f, 0.f);
+    }
+    const int segw = G.nv * (G.LW + 2 * SEG_PAD);
+    for (int i = tid; i < n_rows(GRAD) * segw; i += nt) {
+        const int row = i / segw, k = i - row * segw;
+        S.rows[(size_t)row * SROW + k] = 0.f;
+    }
+}
+
+// ---- loads of a thread's own row --------------------------------------------
+template <bool MASKED>
+USL_HD void c_load_row(const LossParams& P, const CState& T, int r, float* x,
+                       float& d, float& u) {
+    if ((MASKED && !T.active) || r < 0 || r >= P.h) return;
+    const unsigned ro = (unsigned)(r * P.w);
+    const float* im = P.img + (T.o_img + ro);
+    x[0] = USL_LDG(im);
+    x[1] = USL_LDG(im + P.img_cs);
+    x[2] = USL_LDG(im + 2 * P.img_cs);
+    d = USL_LDG(P.disp + (T.o_d + ro));
+    if (P.unc) u = USL_LDG(P.unc + (T.o_u + ro));
+}
+
+// opposite view {r,g,b,disparity} of image row `row` at the thread's column
+USL_HD void c_load_opp(const LossParams& P, unsigned o_oi, unsigned o_od,
+                       int row, float* o4) {
+    const unsigned ro = (unsigned)(row * P.w);
+    const float* im = P.img + (o_oi + ro);
+    o4[0] = USL_LDG(im);
+    o4[1] = USL_LDG(im + P.img_cs);
+    o4[2] = USL_LDG(im + 2 * P.img_cs);
+    o4[3] = USL_LDG(P.disp + (o_od + ro));
+}
+
+// ---- V(r): vertical blend of the opposite view, whole row --------------------
+// Full-row units: thread (vi, lc) produces its own column.  Column-tiled units:
+// the threads of the unit sweep the whole row.
+template <bool TILED, bool MASKED>
+USL_HD void c_pV(const LossParams& P, const CGeo& G, const CRings& S, int r,
+                 int tid, int nt, const CState& T) {
+    if (r < 0 || r >= P.h) return;
+    const RowV t = S.RV[r - (G.ya - 2)];
+    if (!TILED) {
+        if (MASKED && !T.active) return;
+        float a[4], b[4];
+        c_load_opp(P, T.o_oi, T.o_od, t.i0, a);
+        c_load_opp(P, T.o_oi, T.o_od, t.i1, b);
+        st_f4(const_cast<F4*>(T.vrow0) + T.c,
+              t.w0 * a[0] + t.w1 * b[0], t.w0 * a[1] + t.w1 * b[1],
+              t.w0 * a[2] + t.w1 * b[2], t.w0 * a[3] + t.w1 * b[3]);
+    } else {
+        for (int it = tid; it < G.nv * P.w; it += nt) {
+            const int vi = it / P.w, x = it - vi * P.w;
+            const int v = G.v0 + vi;
+            const unsigned oi = (unsigned)((long long)G.b * P.img_bs +
+                                           (long long)(1 - v) * 3 * P.img_cs + x);
+            const unsigned od = (unsigned)((long long)G.b * P.d_bs +
+                                           (long long)(1 - v) * P.d_cs + x);
+            float a[4], b[4];
+            c_load_opp(P, oi, od, t.i0, a);
+            c_load_opp(P, oi, od, t.i1, b);
+            st_f4(S.V + (size_t)vi * (P.w + 2 * VPAD) + VPAD + x,
+                  t.w0 * a[0] + t.w1 * b[0], t.w0 * a[1] + t.w1 * b[1],
+                  t.w0 * a[2] + t.w1 * b[2], t.w0 * a[3] + t.w1 * b[3]);
+        }
+    }
+}
+
+USL_HD float edge_w3(const float* a, const float* b) {
+    const float g = fabsf(a[0] - b[0]) + fabsf(a[1] - b[1]) + fabsf(a[2] - b[2]);
+    return fast_exp2(g * (-LOG2E / 3.0f));
+}
+
+// ---- P1: warp of row r, row-local terms ---------------------------------------
+// MASKED: some threads of the unit hold no column / halo columns (tiles, widths
+// that are not a multiple of the warp size).
+template <int SROW, bool GRAD, bool MASKED>
+USL_HD void c_p1(const LossParams& P, const CGeo& G, int r, CState& T) {
+    if (GRAD) {
+        T.gd[2] = T.gd[1]; T.gd[1] = T.gd[0]; T.gd[0] = 0.f;
+        T.gu[2] = T.gu[1]; T.gu[1] = T.gu[0]; T.gu[0] = 0.f;
+    }
+    if ((MASKED && !T.active) || r < 0 || r >= P.h) return;
+    const int nh = GRAD ? NHIST_GRAD : NHIST_FWD;
+    const float sign = T.sign, fw = (float)P.w, hw = 0.5f * fw;
+    const unsigned terms = P.terms;
+    const bool own_row = r >= G.ya && r < G.yb;
+    const float own = MASKED ? T.own : 1.0f;
+    float* hs = T.sb + (ROW_HS + mod3(r) * nh) * SROW;
+
+    // ---- reconstruction of the row: two taps of V at the shifted column ----
+    float wd, dwd = 0.f, dI[3];
+    {
+        const float ix = c_warp_coord(T.xbase, sign * T.d, hw);
+        const float f = floorf(ix);
+        const float w1 = ix - f, w0 = (f + 1.0f) - ix;
+        const int xi = (int)fminf(fmaxf(f, -2.0f), fw);
+        const F4 t0 = ld_f4(T.vrow0 + xi), t1 = ld_f4(T.vrow0 + xi + 1);
+        T.y[0] = w0 * t0.x + w1 * t1.x;
+        T.y[1] = w0 * t0.y + w1 * t1.y;
+        T.y[2] = w0 * t0.z + w1 * t1.z;
+        wd = w0 * t0.w + w1 * t1.w;
+        if (GRAD) {
+            dI[0] = fw * (t1.x - t0.x);
+            dI[1] = fw * (t1.y - t0.y);
+            dI[2] = fw * (t1.z - t0.z);
+            dwd = fw * (t1.w - t0.w);
+        }
+    }
+    float l1 = 0.f, gl1 = 0.f;
+    for (int c = 0; c < 3; ++c) {
+        const float a = T.x[c] - T.y[c];
+        l1 += fabsf(a);
+        T.sb[(ROW_Y + c) * SROW] = T.y[c];
+        T.sb[(ROW_X + c) * SROW] = T.x[c];
+        if (GRAD) {
+            gl1 += sgn_mul(a, dI[c]);
+            hs[c * SROW] = dI[c];
+            hs[(3 + c) * SROW] = T.y[c] * dI[c];
+            hs[(6 + c) * SROW] = T.x[c] * dI[c];
+        }
+    }
+    T.sb[(ROW_DU + 0) * SROW] = T.d;
+    T.sb[(ROW_DU + 1) * SROW] = T.u;
+    hs[(nh - 2) * SROW] = l1;
+    hs[(nh - 1) * SROW] = T.u;
+    if (!GRAD && P.recon_out && own_row && own != 0.f) {
+        const long long hwp = (long long)P.h * P.w;
+        for (int c = 0; c < 3; ++c)
+            P.recon_out[((long long)G.b * 6 + T.v * 3 + c) * hwp +
+                        (long long)r * P.w + T.c] = T.y[c];
+    }
+
+    if (own_row) {
+        float gdr = 0.f, gur = 0.f;
+        if (GRAD) {
+            // L1 part of d reproj / d recon, through the warp
+            const float kl1 = G.gd_up * P.coef[ACC_REPROJ] * (1.0f - P.alpha) *
+                              (1.0f / 3.0f);
+            gdr = (-sign * kl1) * gl1;
+        }
+        // ---- consistency terms ----
+        if (terms & TERM_CONS_D) {
+            const float f = T.d - wd;
+            T.acc[ACC_CONS_D] += own * fabsf(f);
+            if (GRAD)
+                gdr += sgn_mul(f, G.gd_up * P.coef[ACC_CONS_D]) *
+                       (1.0f - sign * dwd);
+        }
+        if (terms & TERM_CONS_U) {
+            const float ix = c_warp_coord(T.xbase, sign * T.u, hw);
+            const float f = floorf(ix);
+            const float w1 = ix - f, w0 = (f + 1.0f) - ix;
+            const int xi = (int)fminf(fmaxf(f, -2.0f), fw);
+            const float g0 = T.vrow0[xi].w, g1 = T.vrow0[xi + 1].w;
+            const float e = T.u - (w0 * g0 + w1 * g1);
+            T.acc[ACC_CONS_U] += own * fabsf(e);
+            if (GRAD)
+                gur = sgn_mul(e, G.ge_up * P.coef[ACC_CONS_U]) *
+                      (1.0f - (sign * fw) * (g1 - g0));
+        }
+        if (GRAD) { T.gd[0] = gdr; T.gu[0] = gur; }
+    }
+
+    // ---- smoothness: vertical edge (r-1, r) of column c ----
+    if (terms & (TERM_SMOOTH_D | TERM_SMOOTH_U)) {
+        const bool prev_own = r - 1 >= G.ya && r - 1 < G.yb;   // implies r >= 1
+        if ((own_row || prev_own) && r >= 1) {
+            const float wy = edge_w3(T.xp, T.x);
+            const float po = prev_own ? own : 0.f;
+            if (terms & TERM_SMOOTH_D) {
+                const float g = T.dp - T.d;
+                T.acc[ACC_SMOOTH_D] += po * (fabsf(g) * wy);
+                if (GRAD) {
+                    const float s = sgn_mul(g, (G.gd_up * P.coef[ACC_SMOOTH_D]) * wy);
+                    if (prev_own) T.gd[1] += s;
+                    if (own_row) T.gd[0] -= s;
+                }
+            }
+            if (terms & TERM_SMOOTH_U) {
+                const float g = T.up - T.u;
+                T.acc[ACC_SMOOTH_U] += po * (fabsf(g) * wy);
+                if (GRAD) {
+                    const float s = sgn_mul(g, (G.ge_up * P.coef[ACC_SMOOTH_U]) * wy);
+                    if (prev_own) T.gu[1] += s;
+                    if (own_row) T.gu[0] -= s;
+                }
+            }
+        }
+    }
+}
+
+// ---- P2: horizontal edges of row r; SSIM of window row q = r - 2 --------------
+// PAR = r & 1 (compile time): T.H[PAR] holds the older history row and takes
+// the new one.
+template <int SROW, bool GRAD, bool MASKED, int PAR>
+USL_HD void c_p2(const LossParams& P, const CGeo& G, const CRings& S, int r,
+                 CState& T) {
+    if (MASKED && !T.active) return;
+    const int q = r - 2;
+    const bool row_ok = r >= 0 && r < P.h;
+    const bool own_row = r >= G.ya && r < G.yb;
+    const float own = MASKED ? T.own : 1.0f;
+    float x1[3], h[3][4];
+    if (row_ok) {
+        for (int c = 0; c < 3; ++c) {
+            const float* yr = T.sb + (ROW_Y + c) * SROW;
+            const float* xr = T.sb + (ROW_X + c) * SROW;
+            const float y0 = T.y[c], y1 = yr[1], y2 = yr[2];
+            const float x0 = T.x[c], x2 = xr[2];
+            x1[c] = xr[1];
+            h[c][0] = x0 + (x1[c] + x2);
+            h[c][1] = y0 + (y1 + y2);
+            const float q0 = fmaf(x0, x0, y0 * y0), q1 = fmaf(x1[c], x1[c], y1 * y1);
+            const float q2 = fmaf(x2, x2, y2 * y2);
+            h[c][2] = q0 + (q1 + q2);
+            h[c][3] = fmaf(x0, y0, fmaf(x1[c], y1, x2 * y2));
+        }
+    } else {
+        for (int c = 0; c < 3; ++c) {
+            x1[c] = 0.f;
+            for (int m = 0; m < 4; ++m) h[c][m] = 0.f;
+        }
+    }
+    // ---- smoothness: edge (c, c+1) of row r (zero in the last column) ----
+    if (own_row && (P.terms & (TERM_SMOOTH_D | TERM_SMOOTH_U))) {
+        const float wx = T.has1 ? edge_w3(T.x, x1) : 0.f;
+        float ed = 0.f, eu = 0.f;
+        if (P.terms & TERM_SMOOTH_D) {
+            const float g = T.d - T.sb[(ROW_DU + 0) * SROW + 1];
+            T.acc[ACC_SMOOTH_D] += own * (fabsf(g) * wx);
+            if (GRAD) {
+                ed = sgn_mul(g, (G.gd_up * P.coef[ACC_SMOOTH_D]) * wx);
+                T.gd[0] += ed;
+            }
+        }
+        if (P.terms & TERM_SMOOTH_U) {
+            const float g = T.u - T.sb[(ROW_DU + 1) * SROW + 1];
+            T.acc[ACC_SMOOTH_U] += own * (fabsf(g) * wx);
+            if (GRAD) {
+                eu = sgn_mul(g, (G.ge_up * P.coef[ACC_SMOOTH_U]) * wx);
+                T.gu[0] += eu;
+            }
+        }
+        if (GRAD) {
+            T.sb[(row_ed(true) + 0) * SROW] = ed;
+            T.sb[(row_ed(true) + 1) * SROW] = eu;
+        }
+    }
+    const bool q_ok = q >= G.qlo && q <= P.h - 3;
+    if (q_ok) {
+        const float inv9 = 1.0f / 9.0f;
+        float kt = 0.f;
+        if (GRAD)      // d reproj / d dssim(q) = coef * alpha/3 * T(q), times -1/2
+            kt = (-0.5f * G.gd_up * P.coef[ACC_REPROJ] * P.alpha * (1.0f / 3.0f) *
+                  inv9 * S.RT[r - (G.ya - 2)].tyw) * T.txw;
+        float dsum = 0.f;
+        for (int c = 0; c < 3; ++c) {
+            const float sx = T.H[0][c][0] + T.H[1][c][0] + h[c][0];
+            const float sy = T.H[0][c][1] + T.H[1][c][1] + h[c][1];
+            const float sq = T.H[0][c][2] + T.H[1][c][2] + h[c][2];
+            const float sxy = T.H[0][c][3] + T.H[1][c][3] + h[c][3];
+            const float mx = inv9 * sx, my = inv9 * sy;
+            const float mm = mx * my;
+            const float m2 = fmaf(mx, mx, my * my);
+            const float n1 = fmaf(2.0f, mm, P.c1);
+            const float d1 = m2 + P.c1;
+            const float d2 = fmaf(inv9, sq, -m2) + P.c2;      // var_x + var_y + c2
+            const float n2 = fmaf(2.0f, fmaf(inv9, sxy, -mm), P.c2);
+            const float inv = fast_rcp(d1 * d2);
+            const float ssim = (n1 * n2) * inv;
+            const float raw = fmaf(-0.5f, ssim, 0.5f);
+            const float cl = fminf(fmaxf(raw, 0.0f), 1.0f);
+            dsum += T.win_ok ? cl : 0.f;
+            if (GRAD) {
+                // the clamp passes the gradient on the closed interval
+                const float gb = (T.win_ok && raw >= 0.0f && raw <= 1.0f) ? kt : 0.0f;
+                // dssim/dA = 2 mx (n2 - n1) inv - 2 my nn (d2 - d1) inv^2
+                const float t1 = (2.0f * mx) * (n2 - n1);
+                const float t2 = (2.0f * my) * (ssim * (d2 - d1));
+                float* gx = T.sb + (row_gx(true) + c * 3) * SROW;
+                gx[0] = gb * ((t1 - t2) * inv);
+                gx[SROW] = (-2.0f * gb) * (ssim * (inv * d1));   // 2 y dssim/dQ: the 2
+                gx[2 * SROW] = gb * (2.0f * (n1 * inv));
+            }
+        }
+        T.sb[(ROW_DS + mod4(q)) * SROW] = dsum;
+    }
+    for (int c = 0; c < 3; ++c)
+        for (int m = 0; m < 4; ++m) T.H[PAR][c][m] = h[c][m];
+}
+
+// ---- P3: everything that needs G(q) / the error map; row r - 2 ---------------
+template <int SROW, bool GRAD, bool MASKED, int PAR>
+USL_HD void c_p3(const LossParams& P, const CGeo& G, const CRings& S, int r,
+                 CState& T) {
+    if (MASKED && !T.active) return;
+    const int nh = GRAD ? NHIST_GRAD : NHIST_FWD;
+    const int y = r - 2;
+    const bool own_row = y >= G.ya && y < G.yb;
+    const bool mine = own_row && (!MASKED || T.own != 0.f);
+    const float* hs = T.sb + (ROW_HS + mod3(y) * nh) * SROW;
+    const unsigned ro = (unsigned)(y * P.w);
+    if (GRAD) {
+        // the left neighbour's right edge of row r lands on this column
+        if (r >= G.ya && r < G.yb && (P.terms & (TERM_SMOOTH_D | TERM_SMOOTH_U))) {
+            T.gd[0] -= T.sb[(row_ed(true) + 0) * SROW - 1];
+            T.gu[0] -= T.sb[(row_ed(true) + 1) * SROW - 1];
+        }
+        const bool q_ok = y >= G.qlo && y <= P.h - 3;
+        float hg[9];
+        if (q_ok) {
+            for (int k = 0; k < 9; ++k) {
+                const float* g = T.sb + (row_gx(true) + k) * SROW;
+                hg[k] = (g[-2] + g[-1]) + g[0];          // windows c-2, c-1, c
+            }
+        } else {
+            for (int k = 0; k < 9; ++k) hg[k] = 0.f;
+        }
+        if (mine) {
+            float gs = 0.f;
+            for (int c = 0; c < 3; ++c) {
+                const float a = hs[c * SROW];
+                const float sA = T.HG[0][c][0] + T.HG[1][c][0] + hg[c * 3 + 0];
+                const float sQ = T.HG[0][c][1] + T.HG[1][c][1] + hg[c * 3 + 1];
+                const float sC = T.HG[0][c][2] + T.HG[1][c][2] + hg[c * 3 + 2];
+                gs = fmaf(a, sA, gs);
+                gs = fmaf(hs[(3 + c) * SROW], sQ, gs);
+                gs = fmaf(hs[(6 + c) * SROW], sC, gs);
+                if (P.grad_recon_in)
+                    gs = fmaf(USL_LDG(P.grad_recon_in +
+                                      ((long long)G.b * 6 + T.v * 3 + c) *
+                                          ((long long)P.h * P.w) + ro + T.c), a, gs);
+            }
+            T.gd[2] += T.sign * gs;
+        }
+        for (int c = 0; c < 3; ++c)
+            for (int m = 0; m < 3; ++m) T.HG[PAR][c][m] = hg[c * 3 + m];
+    }
+    if (!mine) return;
+    // error map row y: bilinear (h-2, w-2) -> (h, w) of dssim, plus L1
+    const RowT rt = S.RT[r - (G.ya - 2)];
+    const float* d0 = T.sb + rt.ay_o0;
+    const float* d1 = T.sb + rt.ay_o1;
+    const float cw1 = T.axw, cw0 = 1.0f - cw1;
+    const float up0 = cw0 * d0[T.ax0] + cw1 * d0[T.ax1];
+    const float up1 = cw0 * d1[T.ax0] + cw1 * d1[T.ax1];
+    const float up = (1.0f - rt.ay_w1) * up0 + rt.ay_w1 * up1;
+    const float l1 = hs[(nh - 2) * SROW];
+    const float e = (P.alpha * up + (1.0f - P.alpha) * l1) * (1.0f / 3.0f);
+    T.acc[ACC_REPROJ] += e;
+    float gur = 0.f;
+    if (P.terms & TERM_UNC) {
+        const float u = hs[(nh - 1) * SROW];
+        if (P.loss_type == LOSS_L1) {
+            const float f = u - e;
+            T.acc[ACC_UNC] += fabsf(f);
+            if (GRAD) gur = sgn_mul(f, G.ge_up * P.coef[ACC_UNC]);
+        } else if (P.loss_type == LOSS_BAYESIAN) {
+            const float iu = fast_rcp(u);
+            T.acc[ACC_UNC] += fmaf(e, iu, LN2 * fast_log2(u));
+            if (GRAD) gur = (G.ge_up * P.coef[ACC_UNC]) * (iu - e * iu * iu);
+        } else {
+            const float eu = e * fast_exp2(u * LOG2E);
+            T.acc[ACC_UNC] += eu + u;
+            if (GRAD) gur = (G.ge_up * P.coef[ACC_UNC]) * (eu + 1.0f);
+        }
+    }
+    if (P.err_out)
+        P.err_out[((long long)G.b * 2 + T.v) * ((long long)P.h * P.w) + ro + T.c] = e;
+    if (GRAD) {
+        float* od = P.grad_disp + (T.o_gd + ro);
+        float* ou = P.grad_unc + (T.o_gu + ro);
+        float a = T.gd[2];
+        if (P.grad_disp_accumulate) a += *od;
+        *od = a;
+        *ou = T.gu[2] + gur;
+    }
+}
+
+// end of a step: the rows move down by one
+USL_HD void c_advance(CState& T) {
+    for (int c = 0; c < 3; ++c) { T.xp[c] = T.x[c]; T.x[c] = T.xn[c]; }
+    T.up = T.u; T.u = T.un;
+    T.dp = T.d; T.d = T.dn;
+}
+
+}  // namespace ck
+}  // namespace usl

@@ -8,6 +8,7 @@
 // CTAs start first and the small scales fill the tail of the wave).
 #include <stdlib.h>
 
+#include "col_launch.cuh"
 #include "cons_core.cuh"
 #include "march_launch.cuh"
 #include "usl_common.cuh"
@@ -298,6 +299,19 @@ extern "C" int usl_loss_plan(const UslLossConfig* cfgs,
                              int mode, int* cta_starts) {
     if (!cfgs || !scales || !cta_starts) return USL_ERR_ARG;
     if (mode != USL_MODE_FWD && mode != USL_MODE_GRAD) return USL_ERR_ARG;
+    if (col_eligible(cfgs, scales, n_scales)) {
+        ColPlan M;
+        M.n = n_scales;
+        int rc = fill_all(cfgs, scales, n_scales, false, M.P);
+        if (rc != USL_OK) return rc;
+        rc = col_plan(&M, mode == USL_MODE_GRAD);
+        if (rc == USL_OK) {
+            // one row of partial sums per unit
+            for (int i = 0; i <= n_scales; ++i) cta_starts[i] = M.row_start[i];
+            return USL_OK;
+        }
+        if (rc != USL_ERR_UNSUPPORTED) return rc;
+    }
     if (march_eligible(cfgs, scales, n_scales)) {
         MarchPlan M;
         M.n = n_scales;
@@ -327,6 +341,32 @@ extern "C" int usl_loss_fwd_ctas(const UslLossScale* s) {
     int TW, R;
     choose_tiling(s->h, s->w, false, &TW, &R);
     return ((s->w + TW - 1) / TW) * ((s->h + R - 1) / R) * s->B;
+}
+
+// The column-marching path, if every scale qualifies: 1 = launched (or failed
+// with *rc_out set), 0 = not eligible.
+static int try_col(const UslLossConfig* cfgs, const UslLossScale* scales,
+                   int n, bool grad, float* partials, const float* gout_d,
+                   const float* gout_e, int accumulate, int skip_if_unit,
+                   cudaStream_t st, int* rc_out) {
+    if (!col_eligible(cfgs, scales, n)) return 0;
+    ColPlan M;
+    M.n = n;
+    int rc = fill_all(cfgs, scales, n, false, M.P);
+    if (rc != USL_OK) { *rc_out = rc; return 1; }
+    rc = col_plan(&M, grad);
+    if (rc == USL_ERR_UNSUPPORTED) return 0;
+    if (rc != USL_OK) { *rc_out = rc; return 1; }
+    for (int i = 0; i < n; ++i) {
+        LossParams& p = M.P[i];
+        p.partials = partials ? partials + (long long)M.row_start[i] * NUM_ACC : nullptr;
+        p.gout_d = gout_d; p.gout_e = gout_e;
+        p.grad_disp_accumulate =
+            (accumulate && (p.terms & (TERM_CONS_D | TERM_CONS_U))) ? 1 : 0;
+        if (grad && (!p.grad_disp || !p.grad_unc)) { *rc_out = USL_ERR_ARG; return 1; }
+    }
+    *rc_out = col_launch(&M, grad, skip_if_unit, st);
+    return 1;
 }
 
 // The marching path, if every scale qualifies: 1 = launched, 0 = not eligible.
@@ -361,6 +401,9 @@ extern "C" int usl_loss_fwd(const UslLossConfig* cfgs,
                             float* partials, void* stream) {
     if (!partials) return USL_ERR_ARG;
     int rc = USL_OK;
+    if (try_col(cfgs, scales, n_scales, false, partials, nullptr, nullptr, 0,
+                0, (cudaStream_t)stream, &rc))
+        return rc;
     if (try_march(cfgs, scales, n_scales, false, partials, nullptr, nullptr, 0,
                   0, (cudaStream_t)stream, &rc))
         return rc;
@@ -450,7 +493,9 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
                              const UslLossScale* scales, int n_scales,
                              const float* gout_disp, const float* gout_err,
                              float* partials, int flags, void* stream) {
-    if (!march_eligible(cfgs, scales, n_scales)) return USL_ERR_UNSUPPORTED;
+    if (!col_eligible(cfgs, scales, n_scales) &&
+        !march_eligible(cfgs, scales, n_scales))
+        return USL_ERR_UNSUPPORTED;
     LossParams P[USL_MAX_SCALES];
     int rc = fill_all(cfgs, scales, n_scales, false, P);
     if (rc != USL_OK) return rc;
@@ -458,6 +503,9 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
     launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
                    (cudaStream_t)stream, &rc);
     if (rc != USL_OK) return rc;
+    if (try_col(cfgs, scales, n_scales, true, partials, gout_disp, gout_err, 1,
+                skip, (cudaStream_t)stream, &rc))
+        return rc;
     if (!try_march(cfgs, scales, n_scales, true, partials, gout_disp, gout_err,
                    1, skip, (cudaStream_t)stream, &rc))
         return USL_ERR_UNSUPPORTED;
@@ -471,7 +519,8 @@ extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
     if (!(stages & (USL_BWD_STAGE_SCATTER | USL_BWD_STAGE_MAIN)))
         return USL_ERR_ARG;
     int rc = USL_OK;
-    if (march_eligible(cfgs, scales, n_scales)) {
+    if (col_eligible(cfgs, scales, n_scales) ||
+        march_eligible(cfgs, scales, n_scales)) {
         // a NULL upstream gradient means "this output takes no part": 0
         LossParams P[USL_MAX_SCALES];
         rc = fill_all(cfgs, scales, n_scales, false, P);
@@ -481,6 +530,10 @@ extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
                        (cudaStream_t)stream, &rc);
         if (rc != USL_OK) return rc;
         if (!(stages & USL_BWD_STAGE_MAIN)) return USL_OK;
+        if (gout_disp && gout_err &&
+            try_col(cfgs, scales, n_scales, true, nullptr, gout_disp,
+                    gout_err, 1, 0, (cudaStream_t)stream, &rc))
+            return rc;
         if (gout_disp && gout_err &&
             try_march(cfgs, scales, n_scales, true, nullptr, gout_disp,
                       gout_err, 1, 0, (cudaStream_t)stream, &rc))
