@@ -4,6 +4,7 @@
 // same rings, same step order -- with one CState per emulated thread and the
 // threads of a phase executed one after the other.  Never linked into
 // libusl.so and never used by the product.
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -33,37 +34,59 @@ static void to_params(const UslLossConfig* cfg, const UslLossScale* s,
     *P = p;
 }
 
-template <bool GRAD, bool TILED, bool MASKED, int PAR>
+template <class C, int PAR>
 static void step(const LossParams& P, const CGeo& G, const CRings& S, int r,
-                 int r1, int nt, std::vector<CState>& T) {
-    for (int t = 0; t < nt; ++t) {
-        if (r + 1 <= r1)
-            c_load_row<MASKED>(P, T[t], r + 1, T[t].xn, T[t].dn, T[t].un);
-        c_p1<SROW, GRAD, MASKED>(P, G, r, T[t]);
+                 int r1, int ring_last, int nt, std::vector<CState>& T) {
+    if (C::MODE == MODE_PLAIN) {
+        const int row = S.RW[c_step_index(G, r)].issue;
+        if (row >= 0)
+            for (int l = 0; l < 32; ++l) c_ring_issue(P, G, S, C::SROW, row, l);
+    } else if (r + 2 <= ring_last) {
+        for (int t = 0; t < nt; ++t) c_ring_fill<C::SROW, C::MODE>(P, G, T[t], r + 2);
     }
-    for (int t = 0; t < nt; ++t) c_p2<SROW, GRAD, MASKED, PAR>(P, G, S, r, T[t]);
+    for (int t = 0; t < nt; ++t) c_p1<C>(P, G, S, r, T[t]);
+    for (int t = 0; t < nt; ++t) c_p2<C, PAR>(P, G, S, r, T[t]);
     for (int t = 0; t < nt; ++t) {
-        c_p3<SROW, GRAD, MASKED, PAR>(P, G, S, r, T[t]);
-        if (r + 1 <= r1) c_pV<TILED, MASKED>(P, G, S, r + 1, t, nt, T[t]);
-        c_advance(T[t]);
+        c_p3<C, PAR>(P, G, S, r, T[t]);
+        if (C::STEADY || r + 1 <= r1) c_pV<C::SROW, C::MODE, C::STEADY>(P, G, S, r, t, nt, T[t]);
     }
 }
 
-template <bool GRAD, bool TILED, bool MASKED>
-static void unit(const LossParams& P, const CGeo& G, int nt, double* sums) {
-    std::vector<float> arena(c_floats(SROW, P.w, G.nv, P.R, GRAD) + 4);
+template <bool GRAD, int MODE>
+static void unit(const LossParams& P, const CGeo& G, int nt, int terms_ct,
+                 double* sums) {
+    std::vector<float> arena(c_floats(SROW, P.w, G.nv, P.R, GRAD) + 8);
     for (auto& v : arena) v = NAN;   // nothing may be read before it is written
-    const CRings S = c_carve(arena.data(), SROW, P.w, G.nv, P.R, GRAD);
+    // 16-byte aligned like the device arena
+    float* base = arena.data();
+    while ((uintptr_t)base & 15) ++base;
+    const CRings S = c_carve(base, SROW, P.w, G.nv, P.R, GRAD);
     std::vector<CState> T(nt);
-    for (int t = 0; t < nt; ++t) c_thread_init<GRAD>(P, G, S, t, T[t]);
-    for (int t = 0; t < nt; ++t) c_init_unit<SROW, GRAD>(P, G, S, t, nt);
+    for (int t = 0; t < nt; ++t) c_thread_init<SROW, GRAD>(P, G, S, t, T[t]);
+    for (int t = 0; t < nt; ++t) c_init_unit<SROW, GRAD, MODE>(P, G, S, t, nt);
     const int r0 = c_first_row(G), r1 = c_last_row(G);
-    for (int t = 0; t < nt; ++t)
-        c_load_row<MASKED>(P, T[t], r0, T[t].x, T[t].d, T[t].u);
-    for (int t = 0; t < nt; ++t) c_pV<TILED, MASKED>(P, G, S, r0, t, nt, T[t]);
+    const int ring_last = c_last_ring_row(P, G);
+    for (int row = r0 - 1; row <= r0 + 1 && row <= ring_last; ++row) {
+        if (MODE == MODE_PLAIN)
+            for (int l = 0; l < 32; ++l) c_ring_issue(P, G, S, SROW, row, l);
+        else for (int t = 0; t < nt; ++t) c_ring_fill<SROW, MODE>(P, G, T[t], row);
+    }
+    for (int t = 0; t < nt; ++t) c_pV<SROW, MODE, false>(P, G, S, r0 - 1, t, nt, T[t]);
+    const int s_lo = G.ya + 2;
+    const int s_hi = (G.yb - 1 < P.h - 3) ? G.yb - 1 : P.h - 3;
+    using CG = Cfg<SROW, GRAD, MODE, -1, false>;
+    using CS = Cfg<SROW, GRAD, MODE, -1, true>;
+    using HG = Cfg<SROW, GRAD, MODE, 47, false>;
+    using HS = Cfg<SROW, GRAD, MODE, 47, true>;
     for (int r = r0; r <= r1; r += 2) {
-        step<GRAD, TILED, MASKED, 0>(P, G, S, r, r1, nt, T);
-        step<GRAD, TILED, MASKED, 1>(P, G, S, r + 1, r1, nt, T);
+        const bool steady = r >= s_lo && r + 1 <= s_hi;
+        if (terms_ct >= 0) {
+            if (steady) { step<HS, 0>(P, G, S, r, r1, ring_last, nt, T); step<HS, 1>(P, G, S, r + 1, r1, ring_last, nt, T); }
+            else { step<HG, 0>(P, G, S, r, r1, ring_last, nt, T); step<HG, 1>(P, G, S, r + 1, r1, ring_last, nt, T); }
+        } else {
+            if (steady) { step<CS, 0>(P, G, S, r, r1, ring_last, nt, T); step<CS, 1>(P, G, S, r + 1, r1, ring_last, nt, T); }
+            else { step<CG, 0>(P, G, S, r, r1, ring_last, nt, T); step<CG, 1>(P, G, S, r + 1, r1, ring_last, nt, T); }
+        }
     }
     for (int t = 0; t < nt; ++t)
         for (int k = 0; k < NUM_ACC; ++k) sums[k] += T[t].acc[k];
@@ -86,7 +109,7 @@ static int run(const UslLossConfig* cfg, const UslLossScale* s, int maxT,
         tiles = (P.w + TW - 1) / TW;
         LW = TW + 4;
     }
-    if (nv * (LW + 4) > SROW) return -2;
+    if (nv * (LW + 2 * SEG_PAD) > SROW) return -2;
     int strips = (P.h + wantR - 1) / wantR;
     int R = (((P.h + strips - 1) / strips) + 1) & ~1;
     strips = (P.h + R - 1) / R;
@@ -109,9 +132,14 @@ static int run(const UslLossConfig* cfg, const UslLossScale* s, int maxT,
                     G.gd_up = gout ? gout[0] : 1.f; G.ge_up = gout ? gout[1] : 1.f;
                     const int n = nv * G.LW;
                     const int nt = (n + 31) & ~31;
-                    if (tiled) unit<GRAD, true, true>(P, G, nt, sums);
-                    else if (n & 31) unit<GRAD, false, true>(P, G, nt, sums);
-                    else unit<GRAD, false, false>(P, G, nt, sums);
+                    // bulk row copies need 16-byte aligned rows (see col_plan)
+                    const bool al = (P.w % 4 == 0) &&
+                        ((((uintptr_t)P.img | (uintptr_t)P.disp | (uintptr_t)P.unc) & 15) == 0) &&
+                        (((P.img_bs | P.img_cs | P.d_bs | P.d_cs | P.u_bs | P.u_cs) & 3) == 0);
+                    const int hot = ((int)P.terms == 47 && !tiled && !(n & 31) && al && !P.grad_recon_in) ? 47 : -1;
+                    if (tiled) unit<GRAD, MODE_TILED>(P, G, nt, -1, sums);
+                    else if ((n & 31) || !al) unit<GRAD, MODE_MASKED>(P, G, nt, -1, sums);
+                    else unit<GRAD, MODE_PLAIN>(P, G, nt, hot, sums);
                 }
     return 0;
 }

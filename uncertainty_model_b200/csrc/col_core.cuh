@@ -102,25 +102,76 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr int VPAD = 2;         // zero columns on each side of a V row
 
+// ---- async row ring (TMA bulk copies + mbarriers) ---------------------------
+#if defined(__CUDA_ARCH__)
+USL_HD uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+USL_HD void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+USL_HD void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+USL_HD void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes) : "memory");
+}
+USL_HD void bulk_g2s(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+USL_HD void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "USL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra USL_DONE;\n"
+        "bra USL_WAIT;\n"
+        "USL_DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+#else
+USL_HD uint32_t smem_u32(const void*) { return 0; }
+USL_HD void mbar_init(uint64_t*, int) {}
+USL_HD void mbar_fence_init() {}
+USL_HD void mbar_expect_tx(uint64_t*, uint32_t) {}
+USL_HD void bulk_g2s(float* dst, const float* src, uint32_t bytes, uint64_t*) {
+    memcpy(dst, src, bytes);
+}
+USL_HD void mbar_wait(uint32_t, uint32_t) {}
+#endif
+
 // ---- shared-memory layout -----------------------------------------------------
 // One arena per CTA: `SROW` floats per row (compile time); a view's segment of
-// a row is [2 pad | LW columns | 2 pad], the two views side by side.  A thread
-// sits at the same position `sb` in every row, so each access is [sb + imm].
-constexpr int SEG_PAD = 2;
+// a row is [4 pad | LW columns | 4 pad] (16-byte aligned for the bulk copies),
+// the two views side by side.  A thread sits at the same position `sb` in every
+// row, so each access is [sb + imm].
+constexpr int SEG_PAD = 4;
 constexpr int NHIST_GRAD = 11;  // dI[3], y*dI[3], x*dI[3], l1, u
 constexpr int NHIST_FWD = 2;    // l1, u
+constexpr int NSLOT = 3;        // input ring depth (rows r-1 | r, r+1, r+2)
+constexpr int NPL = 5;          // planes per ring slot: x[3], d, u
 enum {
     ROW_Y = 0,      // [3]  recon of the current row        (right neighbours read)
-    ROW_X = 3,      // [3]  own image row                   (right neighbours read)
-    ROW_DU = 6,     // [2]  own disparity, uncertainty      (right neighbour reads)
-    ROW_DS = 8,     // [4]  ring of channel-summed dssim rows
-    ROW_HS = 12,    // [3][NH] thread-private history of the rows in flight
+    ROW_DS = 3,     // [4]  ring of channel-summed dssim rows
+    ROW_IN = 7,     // [NSLOT][NPL] own view(s): image, disparity, uncertainty rows
+    ROW_OPP = 22,   // [NSLOT][NPL] opposite view (one-view units): image, disparity
+    ROW_HS = 37,    // [3][NH] thread-private history of the rows in flight
 };
 USL_HD constexpr int row_gx(bool grad) {     // [9] G(q) of the current window row
     return ROW_HS + 3 * (grad ? NHIST_GRAD : NHIST_FWD);
 }
 USL_HD constexpr int row_ed(bool grad) { return row_gx(grad) + 9; }   // [2]
 USL_HD constexpr int n_rows(bool grad) { return grad ? row_ed(true) + 2 : row_gx(false); }
+
+enum { MODE_PLAIN = 0, MODE_MASKED = 1, MODE_TILED = 2 };
+// MODE_PLAIN : full-row unit, every thread owns a column, inputs arrive by bulk
+//              async copies (needs w % 4 == 0 and 16-byte aligned planes)
+// MODE_MASKED: full-row unit of any width / alignment; the threads fill the ring
+// MODE_TILED : column tile with halos; V(r) swept straight from global memory
 
 struct CGeo {                // per-CTA constants
     int b;                   // sample
@@ -133,40 +184,68 @@ struct CGeo {                // per-CTA constants
     float gd_up, ge_up;      // upstream gradients (GRAD)
 };
 
-// per-step tables (one entry per row of the strip), see c_init_unit
+// per-step tables (entry i: step r = ya - 3 + i; entry 0 only serves the
+// prologue's V(ya - 2)), see c_init_unit
 struct alignas(16) RowT {
     float tyw;               // transposed up-sample row weight of q = r - 2
     float ay_w1;             // up-sample (h-2 -> h) weight of tap i1, y = r - 2
     int ay_o0, ay_o1;        // float offsets (from sb) of the dssim ring rows i0, i1
 };
-struct alignas(16) RowV {    // vertical taps of the warp for row r
-    int i0, i1;              // source rows (clamped into the image)
+struct alignas(16) RowU {
+    int in_o;                // float offset of the input ring slot of row r
+    int hs_w, hs_r;          // ... of the history slots of rows r (write), r-2 (read)
+    int ds_w;                // ... of the dssim ring row of q = r - 2
+};
+struct alignas(16) RowV {    // vertical taps of the warp for row r + 1
+    int o0, o1;              // float offsets of the ring slots of the source rows
     float w0, w1;            // weights (zero for rows outside the image)
+};
+struct alignas(16) RowW {    // ring synchronisation of the step
+    int wait_cur;            // slot | parity << 8 of row r            (-1: none)
+    int wait_v0, wait_v1;    // ... of the two source rows of V(r + 1) (-1: none)
+    int issue;               // row to request at the start of the step (-1: none)
 };
 
 struct CRings {
     float* rows;    // [n_rows][SROW]
     F4* V;          // [nv][w + 2*VPAD]
-    RowT* RT;       // [R + 6]
-    RowV* RV;       // [R + 6]
+    RowT* RT;       // [R + 8] each
+    RowU* RU;
+    RowV* RV;
+    RowW* RW;
+    uint64_t* mbar; // [NSLOT]
+    uint32_t mbar_a;      // shared-window address of mbar[0]
+    const float** isrc;   // [MAX_ISSUE] row 0 of every plane the ring holds
+    int* idst;            // [MAX_ISSUE] float offset of its row inside a slot
 };
+constexpr int MAX_ISSUE = 10;
 
 USL_HD int c_first_row(const CGeo& G) { return G.ya - 2; }
 USL_HD int c_last_row(const CGeo& G) { return G.yb + 1; }
+USL_HD int c_step_index(const CGeo& G, int r) { return r - (G.ya - 3); }
+USL_HD int c_ring_slot(const CGeo& G, int row) { return (row - (G.ya - 3)) % NSLOT; }
+USL_HD int c_ring_parity(const CGeo& G, int row) { return ((row - (G.ya - 3)) / NSLOT) & 1; }
 
 // floats of shared memory for one CTA
 USL_HD size_t c_floats(int srow, int w, int nv, int R, bool grad) {
     size_t n = (size_t)n_rows(grad) * srow;
     n += (size_t)nv * (w + 2 * VPAD) * 4;
-    n += (size_t)(R + 6) * 8;
+    n += (size_t)(R + 8) * 16;
+    n += 8 + 2 * MAX_ISSUE + 12;
     return (n + 3) & ~(size_t)3;
 }
 
 USL_HD CRings c_carve(float* base, int srow, int w, int nv, int R, bool grad) {
     CRings S;
     S.V = reinterpret_cast<F4*>(base); base += (size_t)nv * (w + 2 * VPAD) * 4;
-    S.RT = reinterpret_cast<RowT*>(base); base += (size_t)(R + 6) * 4;
-    S.RV = reinterpret_cast<RowV*>(base); base += (size_t)(R + 6) * 4;
+    S.RT = reinterpret_cast<RowT*>(base); base += (size_t)(R + 8) * 4;
+    S.RU = reinterpret_cast<RowU*>(base); base += (size_t)(R + 8) * 4;
+    S.RV = reinterpret_cast<RowV*>(base); base += (size_t)(R + 8) * 4;
+    S.RW = reinterpret_cast<RowW*>(base); base += (size_t)(R + 8) * 4;
+    S.mbar = reinterpret_cast<uint64_t*>(base); base += 8;
+    S.mbar_a = smem_u32(S.mbar);
+    S.isrc = reinterpret_cast<const float**>(base); base += 2 * MAX_ISSUE;
+    S.idst = reinterpret_cast<int*>(base); base += 12;
     S.rows = base;
     return S;
 }
@@ -174,7 +253,6 @@ USL_HD CRings c_carve(float* base, int srow, int w, int nv, int R, bool grad) {
 struct CState {
     float x[3], d, u;        // own inputs, row r
     float xp[3], dp, up;     // row r-1
-    float xn[3], dn, un;     // row r+1 (in flight)
     float y[3];              // recon of row r                    (P1 -> P2)
     float H[2][3][4];        // horizontal 3-sums of the two previous rows
     float HG[2][3][3];       // ... of G of the two previous window rows
@@ -187,11 +265,12 @@ struct CState {
     float own;               // 1 where the column belongs to the unit
     float sign;              // -1 left view, +1 right view
     float* sb;               // the thread's position in row 0 of the arena
+    const float* ob;         // the same column of the opposite view's ring rows
     const F4* vrow0;         // column 0 of the own view's V row
     int ax0, ax1;            // column offsets (from the own column) of the up-sample taps
     unsigned o_img, o_d, o_u;   // element offsets of (b, own view, row 0, c)
     unsigned o_oi, o_od;        // ... of (b, opposite view, row 0, c): img, disp
-    unsigned o_gd, o_gu;        // ... in the gradient tensors
+    float* p_gd; float* p_gu;   // gradient outputs at (b, own view, row ya, c)
     int v, vi, c, lc;
     bool active, win_ok, has1;
 };
@@ -203,7 +282,7 @@ USL_HD float c_warp_coord(float xbase, float shift, float half_n) {
 }
 
 // ---- CTA prologue -----------------------------------------------------------
-template <bool GRAD>
+template <int SROW, bool GRAD>
 USL_HD void c_thread_init(const LossParams& P, const CGeo& G, const CRings& S,
                           int tid, CState& T) {
     const int w = P.w;
@@ -221,22 +300,28 @@ USL_HD void c_thread_init(const LossParams& P, const CGeo& G, const CRings& S,
         }
     for (int a = 0; a < 3; ++a) T.gd[a] = T.gu[a] = 0.f;
     for (int k = 0; k < NUM_ACC; ++k) T.acc[k] = 0.f;
-    for (int c = 0; c < 3; ++c) T.x[c] = T.xp[c] = T.xn[c] = T.y[c] = 0.f;
-    T.d = T.dp = T.dn = 0.f;
-    T.u = T.up = T.un = 1.f;
+    for (int c = 0; c < 3; ++c) T.x[c] = T.xp[c] = T.y[c] = 0.f;
+    T.d = T.dp = 0.f;
+    T.u = T.up = 1.f;
     T.xbase = linspace01(T.c, w);
     T.own = (T.active && T.c >= G.xa && T.c < G.xb) ? 1.f : 0.f;
     T.win_ok = T.c <= w - 3;
     T.has1 = T.c + 1 < w;
-    T.sb = S.rows + T.vi * (G.LW + 2 * SEG_PAD) + SEG_PAD + T.lc;
+    const int seg = G.LW + 2 * SEG_PAD;
+    T.sb = S.rows + T.vi * seg + SEG_PAD + T.lc;
+    // two-view units: the opposite view is the other segment of the input ring
+    T.ob = G.nv == 2 ? S.rows + (1 - T.vi) * seg + SEG_PAD + T.lc + ROW_IN * SROW
+                     : T.sb + ROW_OPP * SROW;
     T.vrow0 = S.V + T.vi * (w + 2 * VPAD) + VPAD;
     T.o_img = (unsigned)((long long)G.b * P.img_bs + (long long)T.v * 3 * P.img_cs + T.c);
     T.o_oi = (unsigned)((long long)G.b * P.img_bs + (long long)(1 - T.v) * 3 * P.img_cs + T.c);
     T.o_d = (unsigned)((long long)G.b * P.d_bs + (long long)T.v * P.d_cs + T.c);
     T.o_od = (unsigned)((long long)G.b * P.d_bs + (long long)(1 - T.v) * P.d_cs + T.c);
     T.o_u = (unsigned)((long long)G.b * P.u_bs + (long long)T.v * P.u_cs + T.c);
-    T.o_gd = (unsigned)((long long)G.b * P.gd_bs + (long long)T.v * P.gd_cs + T.c);
-    T.o_gu = (unsigned)((long long)G.b * P.gu_bs + (long long)T.v * P.gu_cs + T.c);
+    T.p_gd = P.grad_disp ? P.grad_disp + ((long long)G.b * P.gd_bs + (long long)T.v * P.gd_cs +
+                                          (long long)G.ya * w + T.c) : nullptr;
+    T.p_gu = P.grad_unc ? P.grad_unc + ((long long)G.b * P.gu_bs + (long long)T.v * P.gu_cs +
+                                        (long long)G.ya * w + T.c) : nullptr;
     T.txw = 0.f; T.axw = 0.f; T.ax0 = T.ax1 = 0;
     if (!T.active) return;
     const TapAC ax = ac_taps(T.c, G.sW, w - 2);
@@ -249,14 +334,22 @@ USL_HD void c_thread_init(const LossParams& P, const CGeo& G, const CRings& S,
         T.txw = upsample_transpose_weight(T.c, w - 2, w, G.sW);
 }
 
+// last image row the unit ever reads (own rows to yb+1, warp sources one more)
+USL_HD int c_last_ring_row(const LossParams& P, const CGeo& G) {
+    const int r = G.yb + 2;
+    return r < P.h - 1 ? r : P.h - 1;
+}
+
 // Zeroes the exchange rows (the pads must be zero, the rest is overwritten
-// before it is read) and the V pads; fills the per-row tables.
-template <int SROW, bool GRAD>
+// before it is read) and the V pads; fills the per-step tables; arms the ring.
+template <int SROW, bool GRAD, int MODE>
 USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
                         int tid, int nt) {
     const int R = P.R;
-    for (int i = tid; i < R + 6; i += nt) {
-        const int r = G.ya - 2 + i;         // step
+    const int nh = GRAD ? NHIST_GRAD : NHIST_FWD;
+    const int last = c_last_ring_row(P, G);
+    for (int i = tid; i < R + 8; i += nt) {
+        const int r = G.ya - 3 + i;         // step
         const int y = r - 2;                // row finalised / window row
         RowT t;
         t.tyw = (GRAD && y >= 0 && y <= P.h - 3)
@@ -270,18 +363,36 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
             t.ay_o1 = (ROW_DS + (i1 & 3)) * SROW;
         }
         S.RT[i] = t;
+        RowU u;
+        u.in_o = (ROW_IN + c_ring_slot(G, r) * NPL) * SROW;
+        u.hs_w = (ROW_HS + mod3(r) * nh) * SROW;
+        u.hs_r = (ROW_HS + mod3(y) * nh) * SROW;
+        u.ds_w = (ROW_DS + mod4(y)) * SROW;
+        S.RU[i] = u;
+        // V(r + 1)
         RowV v;
-        v.i0 = v.i1 = 0; v.w0 = v.w1 = 0.f;
-        if (r >= 0 && r < P.h) {
-            const Tap2 ty = warp_row_taps(r, P.h);
+        RowW ww;
+        v.o0 = v.o1 = 0; v.w0 = v.w1 = 0.f;
+        ww.wait_cur = ww.wait_v0 = ww.wait_v1 = ww.issue = -1;
+        const int rn = r + 1;
+        if (rn >= 0 && rn < P.h) {
+            const Tap2 ty = warp_row_taps(rn, P.h);
             const bool ok0 = ty.i0 >= 0 && ty.i0 < P.h;
             const bool ok1 = ty.i0 + 1 >= 0 && ty.i0 + 1 < P.h;
             v.w0 = ok0 ? ty.w0 : 0.0f;
             v.w1 = ok1 ? ty.w1 : 0.0f;
-            v.i0 = ok0 ? ty.i0 : ty.i0 + 1;
-            v.i1 = ok1 ? ty.i0 + 1 : ty.i0;
+            const int i0 = ok0 ? ty.i0 : ty.i0 + 1;
+            const int i1 = ok1 ? ty.i0 + 1 : ty.i0;
+            v.o0 = c_ring_slot(G, i0) * NPL * SROW;
+            v.o1 = c_ring_slot(G, i1) * NPL * SROW;
+            ww.wait_v0 = c_ring_slot(G, i0) | (c_ring_parity(G, i0) << 8);
+            ww.wait_v1 = c_ring_slot(G, i1) | (c_ring_parity(G, i1) << 8);
         }
         S.RV[i] = v;
+        if (r >= 0 && r < P.h)
+            ww.wait_cur = c_ring_slot(G, r) | (c_ring_parity(G, r) << 8);
+        if (r + 2 >= G.ya && r + 2 <= last) ww.issue = r + 2;
+        S.RW[i] = ww;
     }
     for (int i = tid; i < G.nv * 2 * VPAD; i += nt) {
         const int vi = i / (2 * VPAD), k = i - vi * 2 * VPAD;
@@ -293,63 +404,144 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
         const int row = i / segw, k = i - row * segw;
         S.rows[(size_t)row * SROW + k] = 0.f;
     }
+    if (MODE == MODE_PLAIN && tid == 0) {
+        for (int s = 0; s < NSLOT; ++s) mbar_init(S.mbar + s, 1);
+        mbar_fence_init();
+        // the planes of one ring slot: where row 0 of each starts in global
+        // memory, and where its row lands inside the slot
+        const int seg = G.LW + 2 * SEG_PAD;
+        int n = 0;
+        for (int vi = 0; vi < G.nv; ++vi) {
+            const int v = G.v0 + vi;
+            const int dst = ROW_IN * SROW + vi * seg + SEG_PAD;
+            for (int k = 0; k < 3; ++k) {
+                S.isrc[n] = plane(P.img, P.img_bs, P.img_cs, G.b, v * 3 + k);
+                S.idst[n++] = dst + k * SROW;
+            }
+            S.isrc[n] = plane(P.disp, P.d_bs, P.d_cs, G.b, v);
+            S.idst[n++] = dst + 3 * SROW;
+            if (P.unc) {
+                S.isrc[n] = plane(P.unc, P.u_bs, P.u_cs, G.b, v);
+                S.idst[n++] = dst + 4 * SROW;
+            }
+        }
+        if (G.nv == 1) {
+            const int v = 1 - G.v0;
+            const int dst = ROW_OPP * SROW + SEG_PAD;
+            for (int k = 0; k < 3; ++k) {
+                S.isrc[n] = plane(P.img, P.img_bs, P.img_cs, G.b, v * 3 + k);
+                S.idst[n++] = dst + k * SROW;
+            }
+            S.isrc[n] = plane(P.disp, P.d_bs, P.d_cs, G.b, v);
+            S.idst[n++] = dst + 3 * SROW;
+        }
+        for (; n < MAX_ISSUE; ++n) { S.isrc[n] = nullptr; S.idst[n] = 0; }
+    }
 }
 
-// ---- loads of a thread's own row --------------------------------------------
-template <bool MASKED>
-USL_HD void c_load_row(const LossParams& P, const CState& T, int r, float* x,
-                       float& d, float& u) {
-    if ((MASKED && !T.active) || r < 0 || r >= P.h) return;
-    const unsigned ro = (unsigned)(r * P.w);
-    const float* im = P.img + (T.o_img + ro);
-    x[0] = USL_LDG(im);
-    x[1] = USL_LDG(im + P.img_cs);
-    x[2] = USL_LDG(im + 2 * P.img_cs);
-    d = USL_LDG(P.disp + (T.o_d + ro));
-    if (P.unc) u = USL_LDG(P.unc + (T.o_u + ro));
+// ---- the input ring -----------------------------------------------------------
+// Row `row` of the unit's views -> ring slot: image planes, disparity,
+// uncertainty of the own view(s); image planes and disparity of the opposite
+// view for one-view units.  MODE_PLAIN: bulk async copies that complete on the
+// slot's mbarrier.
+USL_HD int c_ring_planes(const LossParams& P, const CGeo& G) {
+    const int n = G.nv == 2 ? 2 * NPL : NPL + 4;
+    return P.unc ? n : n - G.nv;
 }
 
-// opposite view {r,g,b,disparity} of image row `row` at the thread's column
-USL_HD void c_load_opp(const LossParams& P, unsigned o_oi, unsigned o_od,
-                       int row, float* o4) {
+// Called by every lane of ONE warp: lane 0 arms the slot's mbarrier with the
+// byte count, then lane k requests plane k -- one bulk copy per lane, so a
+// whole row set costs the warp a dozen instructions.
+USL_HD void c_ring_issue(const LossParams& P, const CGeo& G, const CRings& S,
+                         int srow, int row, int lane) {
+    if (row >= P.h) return;
+    const int slot = c_ring_slot(G, row);
+    uint64_t* bar = S.mbar + slot;
+    const int n = c_ring_planes(P, G);
+    const unsigned bytes = (unsigned)G.LW * 4u;
+    // a row above the image is never waited for, but its phase must still
+    // complete so that the slot's parity keeps counting uses
+    if (lane == 0) mbar_expect_tx(bar, row < 0 ? 0u : bytes * (unsigned)n);
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+    if (row < 0 || lane >= n) return;
+    bulk_g2s(S.rows + S.idst[lane] + (size_t)slot * NPL * srow,
+             S.isrc[lane] + (long long)row * P.w, bytes, bar);
+}
+
+// MODE_MASKED / MODE_TILED: every thread moves its own column (plain loads).
+template <int SROW, int MODE>
+USL_HD void c_ring_fill(const LossParams& P, const CGeo& G, const CState& T, int row) {
+    if (!T.active || row < 0 || row >= P.h) return;
+    const int slot = c_ring_slot(G, row);
     const unsigned ro = (unsigned)(row * P.w);
-    const float* im = P.img + (o_oi + ro);
-    o4[0] = USL_LDG(im);
-    o4[1] = USL_LDG(im + P.img_cs);
-    o4[2] = USL_LDG(im + 2 * P.img_cs);
-    o4[3] = USL_LDG(P.disp + (o_od + ro));
+    float* dst = T.sb + (ROW_IN + slot * NPL) * SROW;
+    const float* im = P.img + (T.o_img + ro);
+    dst[0] = USL_LDG(im);
+    dst[SROW] = USL_LDG(im + P.img_cs);
+    dst[2 * SROW] = USL_LDG(im + 2 * P.img_cs);
+    dst[3 * SROW] = USL_LDG(P.disp + (T.o_d + ro));
+    if (P.unc) dst[4 * SROW] = USL_LDG(P.unc + (T.o_u + ro));
+    if (MODE != MODE_TILED && G.nv == 1) {
+        float* od = T.sb + (ROW_OPP + slot * NPL) * SROW;
+        const float* oi = P.img + (T.o_oi + ro);
+        od[0] = USL_LDG(oi);
+        od[SROW] = USL_LDG(oi + P.img_cs);
+        od[2 * SROW] = USL_LDG(oi + 2 * P.img_cs);
+        od[3 * SROW] = USL_LDG(P.disp + (T.o_od + ro));
+    }
 }
 
-// ---- V(r): vertical blend of the opposite view, whole row --------------------
-// Full-row units: thread (vi, lc) produces its own column.  Column-tiled units:
-// the threads of the unit sweep the whole row.
-template <bool TILED, bool MASKED>
+// `sure`: the row is known to exist (no test of the table entry)
+template <bool SURE>
+USL_HD void c_ring_wait(const CRings& S, int slot_parity) {
+    if (SURE || slot_parity >= 0)
+        mbar_wait(S.mbar_a + 8u * (unsigned)(slot_parity & 0xff), (unsigned)(slot_parity >> 8));
+}
+
+// ---- V(r+1): vertical blend of the opposite view, whole row -------------------
+// Full-row units: thread (vi, lc) blends its own column from the ring.
+// Column-tiled units: the threads of the unit sweep the whole row from global.
+template <int SROW, int MODE, bool STEADY>
 USL_HD void c_pV(const LossParams& P, const CGeo& G, const CRings& S, int r,
                  int tid, int nt, const CState& T) {
-    if (r < 0 || r >= P.h) return;
-    const RowV t = S.RV[r - (G.ya - 2)];
-    if (!TILED) {
-        if (MASKED && !T.active) return;
-        float a[4], b[4];
-        c_load_opp(P, T.o_oi, T.o_od, t.i0, a);
-        c_load_opp(P, T.o_oi, T.o_od, t.i1, b);
+    const int rn = r + 1;
+    if (!STEADY && (rn < 0 || rn >= P.h)) return;
+    const int i = c_step_index(G, r);
+    const RowV t = S.RV[i];
+    if (MODE != MODE_TILED) {
+        if (MODE == MODE_PLAIN) {
+            const RowW ww = S.RW[i];
+            c_ring_wait<STEADY>(S, ww.wait_v0);
+            c_ring_wait<STEADY>(S, ww.wait_v1);
+        }
+        if (MODE == MODE_MASKED && !T.active) return;
+        const float* a = T.ob + t.o0;
+        const float* b = T.ob + t.o1;
         st_f4(const_cast<F4*>(T.vrow0) + T.c,
-              t.w0 * a[0] + t.w1 * b[0], t.w0 * a[1] + t.w1 * b[1],
-              t.w0 * a[2] + t.w1 * b[2], t.w0 * a[3] + t.w1 * b[3]);
+              t.w0 * a[0] + t.w1 * b[0],
+              t.w0 * a[SROW] + t.w1 * b[SROW],
+              t.w0 * a[2 * SROW] + t.w1 * b[2 * SROW],
+              t.w0 * a[3 * SROW] + t.w1 * b[3 * SROW]);
     } else {
+        const Tap2 ty = warp_row_taps(rn, P.h);
+        const bool ok0 = ty.i0 >= 0 && ty.i0 < P.h;
+        const bool ok1 = ty.i0 + 1 >= 0 && ty.i0 + 1 < P.h;
+        const unsigned r0 = (unsigned)((ok0 ? ty.i0 : ty.i0 + 1) * P.w);
+        const unsigned r1 = (unsigned)((ok1 ? ty.i0 + 1 : ty.i0) * P.w);
         for (int it = tid; it < G.nv * P.w; it += nt) {
             const int vi = it / P.w, x = it - vi * P.w;
             const int v = G.v0 + vi;
-            const unsigned oi = (unsigned)((long long)G.b * P.img_bs +
-                                           (long long)(1 - v) * 3 * P.img_cs + x);
-            const unsigned od = (unsigned)((long long)G.b * P.d_bs +
-                                           (long long)(1 - v) * P.d_cs + x);
-            float a[4], b[4];
-            c_load_opp(P, oi, od, t.i0, a);
-            c_load_opp(P, oi, od, t.i1, b);
+            const float* im = P.img + (unsigned)((long long)G.b * P.img_bs +
+                                                 (long long)(1 - v) * 3 * P.img_cs + x);
+            const float* pd = P.disp + (unsigned)((long long)G.b * P.d_bs +
+                                                  (long long)(1 - v) * P.d_cs + x);
             st_f4(S.V + (size_t)vi * (P.w + 2 * VPAD) + VPAD + x,
-                  t.w0 * a[0] + t.w1 * b[0], t.w0 * a[1] + t.w1 * b[1],
-                  t.w0 * a[2] + t.w1 * b[2], t.w0 * a[3] + t.w1 * b[3]);
+                  t.w0 * USL_LDG(im + r0) + t.w1 * USL_LDG(im + r1),
+                  t.w0 * USL_LDG(im + P.img_cs + r0) + t.w1 * USL_LDG(im + P.img_cs + r1),
+                  t.w0 * USL_LDG(im + 2 * P.img_cs + r0) + t.w1 * USL_LDG(im + 2 * P.img_cs + r1),
+                  t.w0 * USL_LDG(pd + r0) + t.w1 * USL_LDG(pd + r1));
         }
     }
 }
@@ -359,22 +551,50 @@ USL_HD float edge_w3(const float* a, const float* b) {
     return fast_exp2(g * (-LOG2E / 3.0f));
 }
 
+// Compile-time knowledge of a step.  STEADY: an interior step of the strip --
+// rows r-2 .. r+2 exist, r-2 .. r are owned, every window row involved is
+// formed here -- so all row tests fold away.  TERMS >= 0: the term mask is a
+// compile-time constant.
+template <int SROW_, bool GRAD_, int MODE_, int TERMS_, bool STEADY_>
+struct Cfg {
+    static constexpr int SROW = SROW_;
+    static constexpr bool GRAD = GRAD_;
+    static constexpr int MODE = MODE_;
+    static constexpr bool MASKED = MODE_ != MODE_PLAIN;
+    static constexpr int TERMS = TERMS_;
+    static constexpr bool STEADY = STEADY_;
+};
+
 // ---- P1: warp of row r, row-local terms ---------------------------------------
-// MASKED: some threads of the unit hold no column / halo columns (tiles, widths
-// that are not a multiple of the warp size).
-template <int SROW, bool GRAD, bool MASKED>
-USL_HD void c_p1(const LossParams& P, const CGeo& G, int r, CState& T) {
+template <class C>
+USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
+                 CState& T) {
+    constexpr int SROW = C::SROW;
+    constexpr bool GRAD = C::GRAD, MASKED = C::MASKED, STEADY = C::STEADY;
     if (GRAD) {
         T.gd[2] = T.gd[1]; T.gd[1] = T.gd[0]; T.gd[0] = 0.f;
         T.gu[2] = T.gu[1]; T.gu[1] = T.gu[0]; T.gu[0] = 0.f;
     }
-    if ((MASKED && !T.active) || r < 0 || r >= P.h) return;
+    // the row before becomes "previous"
+    for (int c = 0; c < 3; ++c) T.xp[c] = T.x[c];
+    T.dp = T.d; T.up = T.u;
+    if (!STEADY && (r < 0 || r >= P.h)) return;
+    const int i = c_step_index(G, r);
+    if (C::MODE == MODE_PLAIN) c_ring_wait<STEADY>(S, S.RW[i].wait_cur);
+    if (MASKED && !T.active) return;
+    const RowU ru = S.RU[i];
     const int nh = GRAD ? NHIST_GRAD : NHIST_FWD;
     const float sign = T.sign, fw = (float)P.w, hw = 0.5f * fw;
-    const unsigned terms = P.terms;
-    const bool own_row = r >= G.ya && r < G.yb;
+    const unsigned terms = C::TERMS >= 0 ? (unsigned)C::TERMS : P.terms;
+    const bool own_row = STEADY || (r >= G.ya && r < G.yb);
     const float own = MASKED ? T.own : 1.0f;
-    float* hs = T.sb + (ROW_HS + mod3(r) * nh) * SROW;
+    float* hs = T.sb + ru.hs_w;
+    {
+        const float* in = T.sb + ru.in_o;
+        T.x[0] = in[0]; T.x[1] = in[SROW]; T.x[2] = in[2 * SROW];
+        T.d = in[3 * SROW];
+        if (P.unc) T.u = in[4 * SROW];
+    }
 
     // ---- reconstruction of the row: two taps of V at the shifted column ----
     float wd, dwd = 0.f, dI[3];
@@ -400,7 +620,6 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, int r, CState& T) {
         const float a = T.x[c] - T.y[c];
         l1 += fabsf(a);
         T.sb[(ROW_Y + c) * SROW] = T.y[c];
-        T.sb[(ROW_X + c) * SROW] = T.x[c];
         if (GRAD) {
             gl1 += sgn_mul(a, dI[c]);
             hs[c * SROW] = dI[c];
@@ -408,8 +627,6 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, int r, CState& T) {
             hs[(6 + c) * SROW] = T.x[c] * dI[c];
         }
     }
-    T.sb[(ROW_DU + 0) * SROW] = T.d;
-    T.sb[(ROW_DU + 1) * SROW] = T.u;
     hs[(nh - 2) * SROW] = l1;
     hs[(nh - 1) * SROW] = T.u;
     if (!GRAD && P.recon_out && own_row && own != 0.f) {
@@ -452,8 +669,8 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, int r, CState& T) {
 
     // ---- smoothness: vertical edge (r-1, r) of column c ----
     if (terms & (TERM_SMOOTH_D | TERM_SMOOTH_U)) {
-        const bool prev_own = r - 1 >= G.ya && r - 1 < G.yb;   // implies r >= 1
-        if ((own_row || prev_own) && r >= 1) {
+        const bool prev_own = STEADY || (r - 1 >= G.ya && r - 1 < G.yb);   // => r >= 1
+        if (STEADY || ((own_row || prev_own) && r >= 1)) {
             const float wy = edge_w3(T.xp, T.x);
             const float po = prev_own ? own : 0.f;
             if (terms & TERM_SMOOTH_D) {
@@ -481,19 +698,25 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, int r, CState& T) {
 // ---- P2: horizontal edges of row r; SSIM of window row q = r - 2 --------------
 // PAR = r & 1 (compile time): T.H[PAR] holds the older history row and takes
 // the new one.
-template <int SROW, bool GRAD, bool MASKED, int PAR>
+template <class C, int PAR>
 USL_HD void c_p2(const LossParams& P, const CGeo& G, const CRings& S, int r,
                  CState& T) {
+    constexpr int SROW = C::SROW;
+    constexpr bool GRAD = C::GRAD, MASKED = C::MASKED, STEADY = C::STEADY;
     if (MASKED && !T.active) return;
     const int q = r - 2;
-    const bool row_ok = r >= 0 && r < P.h;
-    const bool own_row = r >= G.ya && r < G.yb;
+    const int i = c_step_index(G, r);
+    const bool row_ok = STEADY || (r >= 0 && r < P.h);
+    const bool own_row = STEADY || (r >= G.ya && r < G.yb);
     const float own = MASKED ? T.own : 1.0f;
+    const unsigned terms = C::TERMS >= 0 ? (unsigned)C::TERMS : P.terms;
+    const RowU ru = S.RU[i];
+    const float* in = T.sb + ru.in_o;
     float x1[3], h[3][4];
     if (row_ok) {
         for (int c = 0; c < 3; ++c) {
             const float* yr = T.sb + (ROW_Y + c) * SROW;
-            const float* xr = T.sb + (ROW_X + c) * SROW;
+            const float* xr = in + c * SROW;
             const float y0 = T.y[c], y1 = yr[1], y2 = yr[2];
             const float x0 = T.x[c], x2 = xr[2];
             x1[c] = xr[1];
@@ -511,19 +734,19 @@ USL_HD void c_p2(const LossParams& P, const CGeo& G, const CRings& S, int r,
         }
     }
     // ---- smoothness: edge (c, c+1) of row r (zero in the last column) ----
-    if (own_row && (P.terms & (TERM_SMOOTH_D | TERM_SMOOTH_U))) {
+    if (own_row && (terms & (TERM_SMOOTH_D | TERM_SMOOTH_U))) {
         const float wx = T.has1 ? edge_w3(T.x, x1) : 0.f;
         float ed = 0.f, eu = 0.f;
-        if (P.terms & TERM_SMOOTH_D) {
-            const float g = T.d - T.sb[(ROW_DU + 0) * SROW + 1];
+        if (terms & TERM_SMOOTH_D) {
+            const float g = T.d - in[3 * SROW + 1];
             T.acc[ACC_SMOOTH_D] += own * (fabsf(g) * wx);
             if (GRAD) {
                 ed = sgn_mul(g, (G.gd_up * P.coef[ACC_SMOOTH_D]) * wx);
                 T.gd[0] += ed;
             }
         }
-        if (P.terms & TERM_SMOOTH_U) {
-            const float g = T.u - T.sb[(ROW_DU + 1) * SROW + 1];
+        if (terms & TERM_SMOOTH_U) {
+            const float g = T.u - in[4 * SROW + 1];
             T.acc[ACC_SMOOTH_U] += own * (fabsf(g) * wx);
             if (GRAD) {
                 eu = sgn_mul(g, (G.ge_up * P.coef[ACC_SMOOTH_U]) * wx);
@@ -531,17 +754,17 @@ USL_HD void c_p2(const LossParams& P, const CGeo& G, const CRings& S, int r,
             }
         }
         if (GRAD) {
-            T.sb[(row_ed(true) + 0) * SROW] = ed;
-            T.sb[(row_ed(true) + 1) * SROW] = eu;
+            if (terms & TERM_SMOOTH_D) T.sb[(row_ed(true) + 0) * SROW] = ed;
+            if (terms & TERM_SMOOTH_U) T.sb[(row_ed(true) + 1) * SROW] = eu;
         }
     }
-    const bool q_ok = q >= G.qlo && q <= P.h - 3;
+    const bool q_ok = STEADY || (q >= G.qlo && q <= P.h - 3);
     if (q_ok) {
         const float inv9 = 1.0f / 9.0f;
         float kt = 0.f;
         if (GRAD)      // d reproj / d dssim(q) = coef * alpha/3 * T(q), times -1/2
             kt = (-0.5f * G.gd_up * P.coef[ACC_REPROJ] * P.alpha * (1.0f / 3.0f) *
-                  inv9 * S.RT[r - (G.ya - 2)].tyw) * T.txw;
+                  inv9 * S.RT[i].tyw) * T.txw;
         float dsum = 0.f;
         for (int c = 0; c < 3; ++c) {
             const float sx = T.H[0][c][0] + T.H[1][c][0] + h[c][0];
@@ -568,34 +791,40 @@ USL_HD void c_p2(const LossParams& P, const CGeo& G, const CRings& S, int r,
                 const float t2 = (2.0f * my) * (ssim * (d2 - d1));
                 float* gx = T.sb + (row_gx(true) + c * 3) * SROW;
                 gx[0] = gb * ((t1 - t2) * inv);
-                gx[SROW] = (-2.0f * gb) * (ssim * (inv * d1));   // 2 y dssim/dQ: the 2
+                gx[SROW] = (-2.0f * gb) * (ssim * (inv * d1));   // (2 y) dssim/dQ: the 2
                 gx[2 * SROW] = gb * (2.0f * (n1 * inv));
             }
         }
-        T.sb[(ROW_DS + mod4(q)) * SROW] = dsum;
+        T.sb[ru.ds_w] = dsum;
     }
     for (int c = 0; c < 3; ++c)
         for (int m = 0; m < 4; ++m) T.H[PAR][c][m] = h[c][m];
 }
 
 // ---- P3: everything that needs G(q) / the error map; row r - 2 ---------------
-template <int SROW, bool GRAD, bool MASKED, int PAR>
+template <class C, int PAR>
 USL_HD void c_p3(const LossParams& P, const CGeo& G, const CRings& S, int r,
                  CState& T) {
+    constexpr int SROW = C::SROW;
+    constexpr bool GRAD = C::GRAD, MASKED = C::MASKED, STEADY = C::STEADY;
     if (MASKED && !T.active) return;
     const int nh = GRAD ? NHIST_GRAD : NHIST_FWD;
     const int y = r - 2;
-    const bool own_row = y >= G.ya && y < G.yb;
+    const int i = c_step_index(G, r);
+    const bool own_row = STEADY || (y >= G.ya && y < G.yb);
     const bool mine = own_row && (!MASKED || T.own != 0.f);
-    const float* hs = T.sb + (ROW_HS + mod3(y) * nh) * SROW;
+    const unsigned terms = C::TERMS >= 0 ? (unsigned)C::TERMS : P.terms;
+    const RowU ru = S.RU[i];
+    const float* hs = T.sb + ru.hs_r;
     const unsigned ro = (unsigned)(y * P.w);
     if (GRAD) {
         // the left neighbour's right edge of row r lands on this column
-        if (r >= G.ya && r < G.yb && (P.terms & (TERM_SMOOTH_D | TERM_SMOOTH_U))) {
-            T.gd[0] -= T.sb[(row_ed(true) + 0) * SROW - 1];
-            T.gu[0] -= T.sb[(row_ed(true) + 1) * SROW - 1];
+        if ((STEADY || (r >= G.ya && r < G.yb)) &&
+            (terms & (TERM_SMOOTH_D | TERM_SMOOTH_U))) {
+            if (terms & TERM_SMOOTH_D) T.gd[0] -= T.sb[(row_ed(true) + 0) * SROW - 1];
+            if (terms & TERM_SMOOTH_U) T.gu[0] -= T.sb[(row_ed(true) + 1) * SROW - 1];
         }
-        const bool q_ok = y >= G.qlo && y <= P.h - 3;
+        const bool q_ok = STEADY || (y >= G.qlo && y <= P.h - 3);
         float hg[9];
         if (q_ok) {
             for (int k = 0; k < 9; ++k) {
@@ -615,7 +844,7 @@ USL_HD void c_p3(const LossParams& P, const CGeo& G, const CRings& S, int r,
                 gs = fmaf(a, sA, gs);
                 gs = fmaf(hs[(3 + c) * SROW], sQ, gs);
                 gs = fmaf(hs[(6 + c) * SROW], sC, gs);
-                if (P.grad_recon_in)
+                if (C::TERMS < 0 && P.grad_recon_in)   // (adversarial step: generic variant)
                     gs = fmaf(USL_LDG(P.grad_recon_in +
                                       ((long long)G.b * 6 + T.v * 3 + c) *
                                           ((long long)P.h * P.w) + ro + T.c), a, gs);
@@ -627,7 +856,7 @@ USL_HD void c_p3(const LossParams& P, const CGeo& G, const CRings& S, int r,
     }
     if (!mine) return;
     // error map row y: bilinear (h-2, w-2) -> (h, w) of dssim, plus L1
-    const RowT rt = S.RT[r - (G.ya - 2)];
+    const RowT rt = S.RT[i];
     const float* d0 = T.sb + rt.ay_o0;
     const float* d1 = T.sb + rt.ay_o1;
     const float cw1 = T.axw, cw0 = 1.0f - cw1;
@@ -638,7 +867,7 @@ USL_HD void c_p3(const LossParams& P, const CGeo& G, const CRings& S, int r,
     const float e = (P.alpha * up + (1.0f - P.alpha) * l1) * (1.0f / 3.0f);
     T.acc[ACC_REPROJ] += e;
     float gur = 0.f;
-    if (P.terms & TERM_UNC) {
+    if (terms & TERM_UNC) {
         const float u = hs[(nh - 1) * SROW];
         if (P.loss_type == LOSS_L1) {
             const float f = u - e;
@@ -657,20 +886,14 @@ USL_HD void c_p3(const LossParams& P, const CGeo& G, const CRings& S, int r,
     if (P.err_out)
         P.err_out[((long long)G.b * 2 + T.v) * ((long long)P.h * P.w) + ro + T.c] = e;
     if (GRAD) {
-        float* od = P.grad_disp + (T.o_gd + ro);
-        float* ou = P.grad_unc + (T.o_gu + ro);
+        // rows are finalised in order: the output pointers walk down with them
         float a = T.gd[2];
-        if (P.grad_disp_accumulate) a += *od;
-        *od = a;
-        *ou = T.gu[2] + gur;
+        if (P.grad_disp_accumulate) a += *T.p_gd;
+        *T.p_gd = a;
+        *T.p_gu = T.gu[2] + gur;
+        T.p_gd += P.w;
+        T.p_gu += P.w;
     }
-}
-
-// end of a step: the rows move down by one
-USL_HD void c_advance(CState& T) {
-    for (int c = 0; c < 3; ++c) { T.xp[c] = T.x[c]; T.x[c] = T.xn[c]; }
-    T.up = T.u; T.u = T.un;
-    T.dp = T.d; T.d = T.dn;
 }
 
 }  // namespace ck

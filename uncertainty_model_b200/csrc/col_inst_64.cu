@@ -1,0 +1,6 @@
+// Column-marching loss kernels, block-size class 64 (see col_kernel_impl.cuh).
+#include "col_kernel_impl.cuh"
+
+namespace usl {
+template int col_launch_class<64>(const ColPlan*, int, bool, int, cudaStream_t);
+}

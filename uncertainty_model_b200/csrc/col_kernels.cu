@@ -1,109 +1,16 @@
-// Kernels (1) and (2), hot form: the column-marching fused loss (see
-// col_core.cuh for the algorithm).  This file owns the unit scheduling, the
-// shared-memory arena and the reductions.
+// Host side of the column-marching fused loss kernels (col_core.cuh /
+// col_kernel_impl.cuh): planning of the units of every scale and the launches.
 //
 // One CTA = one unit (sample, row strip, view set, column tile).  Every pyramid
-// scale is its own launch -- block size, row stride and all of the geometry /
-// configuration are then CTA-uniform kernel parameters at fixed constant-bank
-// addresses -- and the launches of a step run concurrently (col_launch forks
-// them over side streams), largest scale first, so the short CTAs of the small
-// scales fill the tail of the large one.
+// scale is its own launch, and the launches of a step run concurrently
+// (col_launch forks them over side streams), largest scale first, so the short
+// CTAs of the small scales fill the tail of the large one.
 #include <stdlib.h>
 
 #include "col_core.cuh"
 #include "col_launch.cuh"
 
 namespace usl {
-
-using namespace ck;
-
-struct ColArgs {
-    LossParams P;
-    int tiles_x, strips, nv;
-    int skip_if_unit;
-};
-
-enum { MODE_PLAIN = 0, MODE_MASKED = 1, MODE_TILED = 2 };
-
-template <int SROW, bool GRAD, bool TILED, bool MASKED, int PAR>
-__device__ __forceinline__ void col_step(const LossParams& P, const CGeo& G,
-                                         const CRings& S, int r, int r_last,
-                                         CState& T) {
-    if (r + 1 <= r_last) c_load_row<MASKED>(P, T, r + 1, T.xn, T.dn, T.un);
-    c_p1<SROW, GRAD, MASKED>(P, G, r, T);
-    __syncthreads();
-    c_p2<SROW, GRAD, MASKED, PAR>(P, G, S, r, T);
-    __syncthreads();
-    c_p3<SROW, GRAD, MASKED, PAR>(P, G, S, r, T);
-    if (r + 1 <= r_last)
-        c_pV<TILED, MASKED>(P, G, S, r + 1, threadIdx.x, blockDim.x, T);
-    c_advance(T);
-    __syncthreads();
-}
-
-template <int SROW, bool GRAD, int MODE>
-__global__ void __launch_bounds__(col_class_threads(SROW), 512 / col_class_threads(SROW))
-col_kernel(const __grid_constant__ ColArgs A) {
-    constexpr bool TILED = MODE == MODE_TILED;
-    constexpr bool MASKED = MODE != MODE_PLAIN;
-    extern __shared__ float4 smem_raw[];
-    __shared__ float red[col_class_threads(SROW) / 32][NUM_ACC];
-
-    const LossParams& P = A.P;
-    CGeo G;
-    G.gd_up = 1.0f; G.ge_up = 1.0f;
-    if (GRAD) {
-        if (P.gout_d) G.gd_up = __ldg(P.gout_d);
-        if (P.gout_e) G.ge_up = __ldg(P.gout_e);
-        if (A.skip_if_unit && G.gd_up == 1.0f && G.ge_up == 1.0f) return;
-    }
-    {
-        int u = blockIdx.x;
-        const int tx = u % A.tiles_x; u /= A.tiles_x;
-        const int nvs = 2 / A.nv;
-        const int vs = u % nvs; u /= nvs;
-        const int st = u % A.strips;
-        G.b = u / A.strips;
-        G.nv = A.nv; G.v0 = vs * A.nv;
-        G.xa = tx * P.TW; G.xb = min(P.w, G.xa + P.TW);
-        G.cbeg = TILED ? max(G.xa - 2, 0) : 0;
-        G.LW = (TILED ? min(G.xb + 2, P.w) : P.w) - G.cbeg;
-        G.ya = st * P.R; G.yb = min(P.h, G.ya + P.R);
-        G.qlo = max(G.ya - 2, 0);
-        G.sH = ac_scale(P.h - 2, P.h); G.sW = ac_scale(P.w - 2, P.w);
-    }
-    const CRings S = c_carve(reinterpret_cast<float*>(smem_raw), SROW, P.w,
-                             G.nv, P.R, GRAD);
-    const int tid = threadIdx.x;
-    CState T;
-    c_thread_init<GRAD>(P, G, S, tid, T);
-    c_init_unit<SROW, GRAD>(P, G, S, tid, blockDim.x);
-    const int r0 = c_first_row(G), r1 = c_last_row(G);
-    c_load_row<MASKED>(P, T, r0, T.x, T.d, T.u);
-    __syncthreads();
-    c_pV<TILED, MASKED>(P, G, S, r0, tid, blockDim.x, T);
-    __syncthreads();
-    // r0 = ya - 2 is even (strip heights are even): PAR is the row parity
-    for (int r = r0; r <= r1; r += 2) {
-        col_step<SROW, GRAD, TILED, MASKED, 0>(P, G, S, r, r1, T);
-        col_step<SROW, GRAD, TILED, MASKED, 1>(P, G, S, r + 1, r1, T);
-    }
-    if (P.partials) {
-        const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-        for (int k = 0; k < NUM_ACC; ++k) {
-            const float v = warp_sum(T.acc[k]);
-            if (lane == 0) red[warp][k] = v;
-        }
-        __syncthreads();
-        if (tid < NUM_ACC) {
-            float t = 0.0f;
-            const int nw = (blockDim.x + 31) >> 5;
-            for (int i = 0; i < nw; ++i) t += red[i][tid];
-            P.partials[(long long)blockIdx.x * NUM_ACC + tid] = t;
-        }
-    }
-}
 
 // ------------------------------------------------------------------ host ---
 static int env_int3(const char* name, int dflt) {
@@ -163,7 +70,13 @@ int col_plan(ColPlan* M, bool grad) {
         if (cls > maxT) return USL_ERR_UNSUPPORTED;
         M->cls[i] = cls;
         M->threads[i] = (nt + 31) & ~31;
-        M->mode[i] = tiles > 1 ? MODE_TILED : ((nt & 31) ? MODE_MASKED : MODE_PLAIN);
+        // bulk async row copies: 16-byte aligned rows of every plane
+        const bool al = (p.w % 4 == 0) &&
+            ((((uintptr_t)p.img | (uintptr_t)p.disp | (uintptr_t)p.unc) & 15) == 0) &&
+            (((p.img_bs | p.img_cs | p.d_bs | p.d_cs | p.u_bs | p.u_cs) & 3) == 0);
+        M->mode[i] = tiles > 1 ? ck::MODE_TILED
+                               : (((nt & 31) || !al || getenv("USL_COL_NO_TMA"))
+                                      ? ck::MODE_MASKED : ck::MODE_PLAIN);
         M->smem[i] = ck::c_floats(col_class_srow(cls), p.w, nv, R, grad) * sizeof(float);
         if (M->smem[i] > 220 * 1024) return USL_ERR_UNSUPPORTED;
         M->row_start[i] = (int)rows;
@@ -173,49 +86,23 @@ int col_plan(ColPlan* M, bool grad) {
     return USL_OK;
 }
 
-template <int SROW, bool GRAD>
-static int launch_class(const ColArgs& A, int mode, int grid, int threads,
-                        size_t smem, cudaStream_t st) {
-#define USL_COL_LAUNCH(MODE)                                                    \
-    do {                                                                        \
-        if (cudaFuncSetAttribute(col_kernel<SROW, GRAD, MODE>,                  \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                 (int)smem) != cudaSuccess)                     \
-            return USL_ERR_CUDA;                                                \
-        col_kernel<SROW, GRAD, MODE><<<grid, threads, smem, st>>>(A);           \
-    } while (0)
-    if (mode == MODE_PLAIN) USL_COL_LAUNCH(MODE_PLAIN);
-    else if (mode == MODE_MASKED) USL_COL_LAUNCH(MODE_MASKED);
-    else {
-        // column tiles only exist in the widest class
-        if constexpr (SROW == col_class_srow(COL_MAX_THREADS)) USL_COL_LAUNCH(MODE_TILED);
-        else return USL_ERR_UNSUPPORTED;
-    }
-#undef USL_COL_LAUNCH
-    return check_launch();
-}
-
-template <bool GRAD>
-static int launch_scale(const ColPlan* M, int i, int skip_if_unit, cudaStream_t st) {
-    ColArgs A;
-    A.P = M->P[i];
-    A.tiles_x = M->tiles_x[i]; A.strips = M->strips[i]; A.nv = M->nv[i];
-    A.skip_if_unit = skip_if_unit;
-    const int grid = M->units[i], nt = M->threads[i];
-    const size_t smem = M->smem[i];
-    switch (M->cls[i]) {
-        case 512: return launch_class<col_class_srow(512), GRAD>(A, M->mode[i], grid, nt, smem, st);
-        case 256: return launch_class<col_class_srow(256), GRAD>(A, M->mode[i], grid, nt, smem, st);
-        case 128: return launch_class<col_class_srow(128), GRAD>(A, M->mode[i], grid, nt, smem, st);
-        case 64: return launch_class<col_class_srow(64), GRAD>(A, M->mode[i], grid, nt, smem, st);
-    }
-    return USL_ERR_UNSUPPORTED;
-}
+template <int CLS>
+int col_launch_class(const ColPlan* M, int i, bool grad, int skip_if_unit,
+                     cudaStream_t st);
+extern template int col_launch_class<512>(const ColPlan*, int, bool, int, cudaStream_t);
+extern template int col_launch_class<256>(const ColPlan*, int, bool, int, cudaStream_t);
+extern template int col_launch_class<128>(const ColPlan*, int, bool, int, cudaStream_t);
+extern template int col_launch_class<64>(const ColPlan*, int, bool, int, cudaStream_t);
 
 int col_launch_scale(const ColPlan* M, int i, bool grad, int skip_if_unit,
                      cudaStream_t st) {
-    return grad ? launch_scale<true>(M, i, skip_if_unit, st)
-                : launch_scale<false>(M, i, skip_if_unit, st);
+    switch (M->cls[i]) {
+        case 512: return col_launch_class<512>(M, i, grad, skip_if_unit, st);
+        case 256: return col_launch_class<256>(M, i, grad, skip_if_unit, st);
+        case 128: return col_launch_class<128>(M, i, grad, skip_if_unit, st);
+        case 64: return col_launch_class<64>(M, i, grad, skip_if_unit, st);
+    }
+    return USL_ERR_UNSUPPORTED;
 }
 
 // Side streams for the concurrent per-scale launches: one small pool per host

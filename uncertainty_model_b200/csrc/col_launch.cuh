@@ -8,6 +8,9 @@
 namespace usl {
 
 constexpr int COL_MAX_THREADS = 512;
+// the term set of the training configuration (config.yml): everything but the
+// smoothness of the uncertainty -- compiled with the term tests folded away
+constexpr int COL_HOT_TERMS = TERM_REPROJ | TERM_CONS_D | TERM_SMOOTH_D | TERM_UNC | TERM_CONS_U;
 
 // Block-size classes: a unit of nv * LW columns runs in the smallest class that
 // holds it; the class fixes the (compile-time) shared-memory row stride.

@@ -33,7 +33,8 @@ struct ConsParams {
     const float* gout_d;                     // device scalars: upstream grads
     const float* gout_e;                     // (NULL = gout_default)
     float gout_default;
-    float* grad_disp; long long gd_bs, gd_cs;  // pure store, both planes
+    float* grad_disp; long long gd_bs, gd_cs;  // both planes
+    int accumulate;                          // add to what is there (else store)
     unsigned terms;                          // TERM_CONS_D | TERM_CONS_U
     float coef_dd, coef_ud;
     int R;                                   // strip height
@@ -152,8 +153,9 @@ USL_HD void cons_phase_D(const ConsParams& P, const ConsTile& T,
             if (rs < 0 || rs >= P.h) continue;
             total += wgt[k] * S.H[((size_t)mod4(rs) * 2 + o) * P.w + x];
         }
-        P.grad_disp[(long long)T.b * P.gd_bs + o * P.gd_cs +
-                    (long long)yd * P.w + x] = total;
+        float* out = P.grad_disp + (long long)T.b * P.gd_bs + o * P.gd_cs +
+                     (long long)yd * P.w + x;
+        *out = P.accumulate ? *out + total : total;
     }
 }
 

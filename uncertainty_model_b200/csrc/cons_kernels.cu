@@ -1,0 +1,160 @@
+// The scattering half of kernel (2): the transposed warp of the consistency
+// terms, deterministic and atomic free.  Arithmetic of cons_core.cuh (see its
+// header for the citations: loss.py:167-188, 430-431); this file is the
+// warp-per-row schedule of it.
+//
+// A CTA owns the destination rows [ya, yb) of one sample; they receive from the
+// source rows [ya-1, yb].  Every (source row, source view) is a JOB done by one
+// warp from start to end, into a row H of shared memory no other warp touches:
+//   * the warp blends the opposite view's disparity row it samples (Vd);
+//   * it walks the row in 32-pixel chunks, in order; the lanes of a chunk that
+//     hit the same destination column are grouped with match.any and summed by
+//     the group leader in lane order; the leaders -- whose destinations are now
+//     distinct -- add into H with plain shared-memory read-modify-writes
+//     (first tap, __syncwarp, second tap).  The order of every sum is a pure
+//     function of the data: no atomics, bit-identical run to run.
+// After ONE block barrier the destination rows are assembled from the three
+// source rows around each of them, with the vertical tap weights, and stored
+// (or added to what the fused kernel wrote before: `accumulate`).
+#include <stdlib.h>
+
+#include "cons_core.cuh"
+#include "cons_launch.cuh"
+#include "usl_common.cuh"
+
+namespace usl {
+
+constexpr int CONS2_THREADS = 384;   // 12 warps: 2 * (16 + 2) jobs = 3 each
+constexpr int HPAD = 2;              // absorbs taps that fall outside the row
+
+// `live`: the lane's taps touch the row; dead lanes carry unique keys (groups
+// of one) and write nothing.
+__device__ __forceinline__ void scatter_chunk(float* Hrow, int d, bool live,
+                                              float a0, float a1, int lane) {
+    unsigned grp = __match_any_sync(0xffffffffu, live ? d : -1000 - lane);
+    const bool leader = (__ffs(grp) - 1) == lane;
+    float s0 = 0.0f, s1 = 0.0f;
+    while (__any_sync(0xffffffffu, grp != 0u)) {
+        const int src = grp ? (__ffs(grp) - 1) : lane;
+        const float v0 = __shfl_sync(0xffffffffu, a0, src);
+        const float v1 = __shfl_sync(0xffffffffu, a1, src);
+        if (grp) { s0 += v0; s1 += v1; grp &= grp - 1; }
+    }
+    if (leader && live) Hrow[d] += s0;
+    __syncwarp();
+    if (leader && live) Hrow[d + 1] += s1;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(CONS2_THREADS)
+cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
+    extern __shared__ float4 smem_raw[];
+    int s = 0;
+    while (s + 1 < M.n && (int)blockIdx.x >= M.cta_start[s + 1]) ++s;
+    const ConsParams& P = M.P[s];
+    const float gd_up = P.gout_d ? __ldg(P.gout_d) : P.gout_default;
+    const float ge_up = P.gout_e ? __ldg(P.gout_e) : P.gout_default;
+    if (M.skip_if_unit && gd_up == 1.0f && ge_up == 1.0f) return;
+    const int local = blockIdx.x - M.cta_start[s];
+    const int b = local / M.strips[s];
+    const int ya = (local % M.strips[s]) * P.R;
+    const int yb = min(P.h, ya + P.R);
+    const int w = P.w, h = P.h;
+    const int HW = w + 2 * HPAD;
+    const int nr = yb - ya + 2;                 // source rows ya-1 .. yb
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    float* H = reinterpret_cast<float*>(smem_raw);        // [nr][2][HW]
+    float* Vall = H + (size_t)(P.R + 2) * 2 * HW;         // [nwarps][HW]
+    float* Vd = Vall + (size_t)warp * HW + HPAD;
+    const float fw = (float)w;
+
+    for (int job = warp; job < 2 * nr; job += nwarps) {
+        const int rsi = job >> 1, v = job & 1, rs = ya - 1 + rsi;
+        float* Hrow = H + ((size_t)rsi * 2 + (1 - v)) * HW + HPAD;
+        for (int x = lane - HPAD; x < w + HPAD; x += 32) Hrow[x] = 0.0f;
+        if (rs < 0 || rs >= h) continue;
+        // blended opposite disparity row for source view v
+        {
+            const Tap2 ty = warp_row_taps(rs, h);
+            const bool ok0 = ty.i0 >= 0 && ty.i0 < h;
+            const bool ok1 = ty.i0 + 1 >= 0 && ty.i0 + 1 < h;
+            const float w0 = ok0 ? ty.w0 : 0.0f, w1 = ok1 ? ty.w1 : 0.0f;
+            const float* pd = plane(P.disp, P.d_bs, P.d_cs, b, 1 - v);
+            const float* p0 = pd + (long long)(ok0 ? ty.i0 : 0) * w;
+            const float* p1 = pd + (long long)(ok1 ? ty.i0 + 1 : 0) * w;
+            for (int x = lane; x < w; x += 32)
+                Vd[x] = w0 * __ldg(p0 + x) + w1 * __ldg(p1 + x);
+            if (lane < HPAD) { Vd[-1 - lane] = 0.0f; Vd[w + lane] = 0.0f; }
+        }
+        __syncwarp();
+        const float sign = v ? 1.0f : -1.0f;
+        for (int term = 0; term < 2; ++term) {
+            if (!(P.terms & (term ? TERM_CONS_U : TERM_CONS_D))) continue;
+            const float* pa = (term ? plane(P.unc, P.u_bs, P.u_cs, b, v)
+                                    : plane(P.disp, P.d_bs, P.d_cs, b, v)) +
+                              (long long)rs * w;
+            const float k = term ? ge_up * P.coef_ud : gd_up * P.coef_dd;
+            for (int base = 0; base < w; base += 32) {
+                const int x = base + lane;
+                const bool valid = x < w;
+                const float a = valid ? __ldg(pa + x) : 0.0f;
+                const Tap2 tx = split_coord(warp_coord(valid ? x : 0, w, sign * a));
+                const int xi = min(max(tx.i0, -HPAD), w);
+                const float f0 = Vd[xi], f1 = Vd[xi + 1];
+                const float f = a - (tx.w0 * f0 + tx.w1 * f1);
+                const float rr = k * sgnf(f);
+                // taps -1 and w land in the pads of the row
+                const bool live = valid && xi >= -1 && xi <= w - 1;
+                scatter_chunk(Hrow, xi, live, -rr * tx.w0, -rr * tx.w1, lane);
+            }
+        }
+    }
+    __syncthreads();
+    // destination rows: H(y'-1), H(y'), H(y'+1) with the vertical tap weights
+    const int per_row = 2 * w;
+    for (int it = tid; it < (yb - ya) * per_row; it += blockDim.x) {
+        const int yi = it / per_row, rem = it - yi * per_row;
+        const int o = rem / w, x = rem - o * w;
+        const int yd = ya + yi;
+        float total = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+            const int rs = yd - 1 + kk;
+            if (rs < 0 || rs >= h) continue;
+            const Tap2 ty = warp_row_taps(rs, h);
+            float wgt = 0.0f;
+            if (ty.i0 == yd) wgt = ty.w0;
+            else if (ty.i0 + 1 == yd) wgt = ty.w1;
+            total += wgt * H[((size_t)(yi + kk) * 2 + o) * HW + HPAD + x];
+        }
+        float* out = P.grad_disp + (long long)b * P.gd_bs + o * P.gd_cs + (long long)yd * w + x;
+        *out = P.accumulate ? *out + total : total;
+    }
+    (void)fw;
+}
+
+int cons_scatter2_launch(MultiCons* C, cudaStream_t st) {
+    // strips of 16 destination rows: 2 * 18 jobs over 12 warps
+    size_t smem = 0;
+    C->cta_start[0] = 0;
+    for (int k = 0; k < C->n; ++k) {
+        ConsParams& c = C->P[k];
+        c.R = 16;
+        if (c.R > c.h) c.R = c.h;
+        C->strips[k] = (c.h + c.R - 1) / c.R;
+        C->cta_start[k + 1] = C->cta_start[k] + C->strips[k] * c.B;
+        const size_t bytes = ((size_t)(c.R + 2) * 2 + CONS2_THREADS / 32) *
+                             (c.w + 2 * HPAD) * sizeof(float);
+        if (bytes > smem) smem = bytes;
+    }
+    if (smem > 220 * 1024) return USL_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(cons_scatter2_kernel,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+        return USL_ERR_CUDA;
+    cons_scatter2_kernel<<<C->cta_start[C->n], CONS2_THREADS, smem, st>>>(*C);
+    return check_launch();
+}
+
+}  // namespace usl

@@ -10,6 +10,7 @@
 
 #include "col_launch.cuh"
 #include "cons_core.cuh"
+#include "cons_launch.cuh"
 #include "march_launch.cuh"
 #include "usl_common.cuh"
 
@@ -20,14 +21,6 @@ struct MultiParams {
     int cta_start[USL_MAX_SCALES + 1];
     int tiles_x[USL_MAX_SCALES], strips[USL_MAX_SCALES];
     int n;
-};
-
-struct MultiCons {
-    ConsParams P[USL_MAX_SCALES];
-    int cta_start[USL_MAX_SCALES + 1];
-    int strips[USL_MAX_SCALES];
-    int n;
-    int skip_if_unit;   // return at once when both upstream gradients are 1
 };
 
 template <bool BWD>
@@ -449,7 +442,7 @@ extern "C" int usl_loss_combine(const double* sums, const float* coef,
 static int launch_scatter(const LossParams* P, int n_scales,
                           const float* gout_disp, const float* gout_err,
                           float gout_default, int skip_if_unit, bool launch,
-                          cudaStream_t st, int* rc_out) {
+                          cudaStream_t st, int* rc_out, int accumulate = 0) {
     MultiCons C;
     C.n = 0; C.cta_start[0] = 0; C.skip_if_unit = skip_if_unit;
     size_t csmem = 0;
@@ -464,6 +457,7 @@ static int launch_scatter(const LossParams* P, int n_scales,
         c.gout_d = gout_disp; c.gout_e = gout_err;
         c.gout_default = gout_default;
         c.grad_disp = p.grad_disp; c.gd_bs = p.gd_bs; c.gd_cs = p.gd_cs;
+        c.accumulate = accumulate;
         c.terms = p.terms & (TERM_CONS_D | TERM_CONS_U);
         c.coef_dd = p.coef[ACC_CONS_D]; c.coef_ud = p.coef[ACC_CONS_U];
         c.R = env_int("USL_CONS_R", 16);
@@ -476,6 +470,17 @@ static int launch_scatter(const LossParams* P, int n_scales,
         if (bytes > csmem) csmem = bytes;
     }
     *rc_out = USL_OK;
+    if (C.n > 0 && launch && !getenv("USL_SCATTER_V1")) {
+        const int rc2 = cons_scatter2_launch(&C, st);
+        if (rc2 != USL_ERR_UNSUPPORTED) { *rc_out = rc2; return C.n; }
+        // (rows too wide for the warp-per-row arena: the strip kernel below)
+        for (int k = 0; k < C.n; ++k) {
+            C.P[k].R = env_int("USL_CONS_R", 16);
+            if (C.P[k].R > C.P[k].h) C.P[k].R = C.P[k].h;
+            C.strips[k] = (C.P[k].h + C.P[k].R - 1) / C.P[k].R;
+            C.cta_start[k + 1] = C.cta_start[k] + C.strips[k] * C.P[k].B;
+        }
+    }
     if (C.n > 0 && launch) {
         if (csmem > 227 * 1024) { *rc_out = USL_ERR_UNSUPPORTED; return C.n; }
         if (cudaFuncSetAttribute(cons_scatter_kernel,
@@ -500,12 +505,18 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
     int rc = fill_all(cfgs, scales, n_scales, false, P);
     if (rc != USL_OK) return rc;
     const int skip = (flags & USL_GRAD_SKIP_IF_UNIT) ? 1 : 0;
+    // column kernels: they store the gradient, then the scatter adds its part
+    // (the read-modify-write sits in the kernel that has warps to spare)
+    if (try_col(cfgs, scales, n_scales, true, partials, gout_disp, gout_err, 0,
+                skip, (cudaStream_t)stream, &rc)) {
+        if (rc != USL_OK) return rc;
+        launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
+                       (cudaStream_t)stream, &rc, 1);
+        return rc;
+    }
     launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
                    (cudaStream_t)stream, &rc);
     if (rc != USL_OK) return rc;
-    if (try_col(cfgs, scales, n_scales, true, partials, gout_disp, gout_err, 1,
-                skip, (cudaStream_t)stream, &rc))
-        return rc;
     if (!try_march(cfgs, scales, n_scales, true, partials, gout_disp, gout_err,
                    1, skip, (cudaStream_t)stream, &rc))
         return USL_ERR_UNSUPPORTED;
