@@ -113,6 +113,11 @@ USL_HD void mbar_init(uint64_t* bar, int count) {
 USL_HD void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// orders the generic-proxy writes of this thread before later async-proxy
+// (bulk copy) accesses to shared memory
+USL_HD void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 USL_HD void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes) : "memory");
@@ -137,6 +142,7 @@ USL_HD void mbar_wait(uint32_t bar, uint32_t parity) {
 USL_HD uint32_t smem_u32(const void*) { return 0; }
 USL_HD void mbar_init(uint64_t*, int) {}
 USL_HD void mbar_fence_init() {}
+USL_HD void fence_proxy_async() {}
 USL_HD void mbar_expect_tx(uint64_t*, uint32_t) {}
 USL_HD void bulk_g2s(float* dst, const float* src, uint32_t bytes, uint64_t*) {
     memcpy(dst, src, bytes);
@@ -404,6 +410,8 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
         const int row = i / segw, k = i - row * segw;
         S.rows[(size_t)row * SROW + k] = 0.f;
     }
+    // the zeros above were generic stores into rows the bulk copies will fill
+    if (MODE == MODE_PLAIN) fence_proxy_async();
     if (MODE == MODE_PLAIN && tid == 0) {
         for (int s = 0; s < NSLOT; ++s) mbar_init(S.mbar + s, 1);
         mbar_fence_init();

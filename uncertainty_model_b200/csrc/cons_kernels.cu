@@ -26,27 +26,37 @@ namespace usl {
 
 constexpr int CONS2_THREADS = 384;   // 12 warps: 2 * (16 + 2) jobs = 3 each
 constexpr int HPAD = 2;              // absorbs taps that fall outside the row
+constexpr int NCH = 16;              // chunks of 32 pixels per span (registers)
 
-// `live`: the lane's taps touch the row; dead lanes carry unique keys (groups
-// of one) and write nothing.
-__device__ __forceinline__ void scatter_chunk(float* Hrow, int d, bool live,
+// One chunk of 32 sources into H.  `d`: destination column of the first tap
+// (dead lanes: a unique key below -1; they write nothing).  Lanes that share a
+// destination form a group (match.any); the contributions of the chunk are
+// staged in shared memory and each group LEADER -- its lowest lane -- adds up
+// those of its group in lane order (a private, collective-free loop), then the
+// leaders, whose destinations are distinct, update H: first taps, then second.
+// `stage`: 32 entries; consecutive calls must alternate between two buffers.
+__device__ __forceinline__ void scatter_chunk(float* Hrow, float2* stage, int d,
                                               float a0, float a1, int lane) {
-    unsigned grp = __match_any_sync(0xffffffffu, live ? d : -1000 - lane);
-    const bool leader = (__ffs(grp) - 1) == lane;
-    float s0 = 0.0f, s1 = 0.0f;
-    while (__any_sync(0xffffffffu, grp != 0u)) {
-        const int src = grp ? (__ffs(grp) - 1) : lane;
-        const float v0 = __shfl_sync(0xffffffffu, a0, src);
-        const float v1 = __shfl_sync(0xffffffffu, a1, src);
-        if (grp) { s0 += v0; s1 += v1; grp &= grp - 1; }
+    const unsigned grp = __match_any_sync(0xffffffffu, d);
+    stage[lane] = make_float2(a0, a1);
+    __syncwarp();
+    const bool leader = d >= -1 && (grp & ((1u << lane) - 1u)) == 0u;
+    if (leader) {
+        float s0 = 0.0f, s1 = 0.0f;
+        for (unsigned m = grp; m; m &= m - 1u) {
+            const float2 c = stage[__ffs(m) - 1];
+            s0 += c.x; s1 += c.y;
+        }
+        Hrow[d] += s0;
+        a1 = s1;
     }
-    if (leader && live) Hrow[d] += s0;
     __syncwarp();
-    if (leader && live) Hrow[d + 1] += s1;
-    __syncwarp();
+    if (leader) Hrow[d + 1] += a1;
+    // (no barrier here: the caller alternates two staging buffers, and the
+    //  barrier after the next chunk's staging orders these updates before its)
 }
 
-__global__ void __launch_bounds__(CONS2_THREADS)
+__global__ void __launch_bounds__(CONS2_THREADS, 2)
 cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
     extern __shared__ float4 smem_raw[];
     int s = 0;
@@ -67,6 +77,10 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
     float* H = reinterpret_cast<float*>(smem_raw);        // [nr][2][HW]
     float* Vall = H + (size_t)(P.R + 2) * 2 * HW;         // [nwarps][HW]
     float* Vd = Vall + (size_t)warp * HW + HPAD;
+    float* xb = Vall + (size_t)nwarps * HW;               // [w] linspace(0,1,w)
+    float2* stage = reinterpret_cast<float2*>(xb + ((w + 3) & ~3)) + warp * 64;
+    for (int x = tid; x < w; x += blockDim.x) xb[x] = linspace01(x, w);
+    __syncthreads();
     const float fw = (float)w;
 
     for (int job = warp; job < 2 * nr; job += nwarps) {
@@ -95,43 +109,80 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
                                     : plane(P.disp, P.d_bs, P.d_cs, b, v)) +
                               (long long)rs * w;
             const float k = term ? ge_up * P.coef_ud : gd_up * P.coef_dd;
-            for (int base = 0; base < w; base += 32) {
-                const int x = base + lane;
-                const bool valid = x < w;
-                const float a = valid ? __ldg(pa + x) : 0.0f;
-                const Tap2 tx = split_coord(warp_coord(valid ? x : 0, w, sign * a));
-                const int xi = min(max(tx.i0, -HPAD), w);
-                const float f0 = Vd[xi], f1 = Vd[xi + 1];
-                const float f = a - (tx.w0 * f0 + tx.w1 * f1);
-                const float rr = k * sgnf(f);
-                // taps -1 and w land in the pads of the row
-                const bool live = valid && xi >= -1 && xi <= w - 1;
-                scatter_chunk(Hrow, xi, live, -rr * tx.w0, -rr * tx.w1, lane);
+            // The row in spans of NCH chunks.  Pass 1 is latency tolerant: all
+            // the loads of a span are in flight together, then destinations
+            // and tap contributions of every pixel go to registers.  Pass 2 is
+            // the ordered part: chunk after chunk into H.
+            for (int span = 0; span < w; span += 32 * NCH) {
+                float c0[NCH], c1[NCH];
+                int dst[NCH];
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int x = span + j * 32 + lane;
+                    c0[j] = x < w ? __ldg(pa + x) : 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int x = span + j * 32 + lane;
+                    const bool valid = x < w;
+                    const float a = c0[j];
+                    // warp_coord(x, w, sign * a) with the base grid from the table
+                    const float g = fmaf(2.0f, xb[valid ? x : 0] + sign * a, -1.0f);
+                    const Tap2 tx = split_coord(fmaf(g + 1.0f, 0.5f * fw, -0.5f));
+                    const int xi = min(max(tx.i0, -HPAD), w);
+                    const float f0 = Vd[xi], f1 = Vd[xi + 1];
+                    const float f = a - (tx.w0 * f0 + tx.w1 * f1);
+                    const float rr = k * sgnf(f);
+                    // taps -1 and w land in the pads of the row; dead lanes get
+                    // unique negative keys
+                    const bool live = valid && xi >= -1 && xi <= w - 1;
+                    dst[j] = live ? xi : -1000 - lane;
+                    c0[j] = -rr * tx.w0;
+                    c1[j] = -rr * tx.w1;
+                }
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    if (span + j * 32 >= w) break;
+                    scatter_chunk(Hrow, stage + (j & 1) * 32, dst[j], c0[j], c1[j], lane);
+                }
             }
         }
     }
     __syncthreads();
     // destination rows: H(y'-1), H(y'), H(y'+1) with the vertical tap weights
-    const int per_row = 2 * w;
-    for (int it = tid; it < (yb - ya) * per_row; it += blockDim.x) {
-        const int yi = it / per_row, rem = it - yi * per_row;
-        const int o = rem / w, x = rem - o * w;
+    // (row by row, so that no thread divides by the width)
+    for (int yi = warp; yi < yb - ya; yi += nwarps) {
         const int yd = ya + yi;
-        float total = 0.0f;
+        float wgt[3];
 #pragma unroll
         for (int kk = 0; kk < 3; ++kk) {
             const int rs = yd - 1 + kk;
+            wgt[kk] = 0.0f;
             if (rs < 0 || rs >= h) continue;
             const Tap2 ty = warp_row_taps(rs, h);
-            float wgt = 0.0f;
-            if (ty.i0 == yd) wgt = ty.w0;
-            else if (ty.i0 + 1 == yd) wgt = ty.w1;
-            total += wgt * H[((size_t)(yi + kk) * 2 + o) * HW + HPAD + x];
+            if (ty.i0 == yd) wgt[kk] = ty.w0;
+            else if (ty.i0 + 1 == yd) wgt[kk] = ty.w1;
         }
-        float* out = P.grad_disp + (long long)b * P.gd_bs + o * P.gd_cs + (long long)yd * w + x;
-        *out = P.accumulate ? *out + total : total;
+        for (int o = 0; o < 2; ++o) {
+            const float* h0 = H + ((size_t)yi * 2 + o) * HW + HPAD;
+            float* out = P.grad_disp + (long long)b * P.gd_bs + o * P.gd_cs + (long long)yd * w;
+            for (int x0 = lane; x0 < w; x0 += 128) {
+                float old[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + 32 * u;
+                    old[u] = (P.accumulate && x < w) ? out[x] : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + 32 * u;
+                    if (x < w)
+                        out[x] = old[u] + (wgt[0] * h0[x] + wgt[1] * h0[2 * HW + x] +
+                                           wgt[2] * h0[4 * HW + x]);
+                }
+            }
+        }
     }
-    (void)fw;
 }
 
 int cons_scatter2_launch(MultiCons* C, cudaStream_t st) {
@@ -144,8 +195,9 @@ int cons_scatter2_launch(MultiCons* C, cudaStream_t st) {
         if (c.R > c.h) c.R = c.h;
         C->strips[k] = (c.h + c.R - 1) / c.R;
         C->cta_start[k + 1] = C->cta_start[k] + C->strips[k] * c.B;
-        const size_t bytes = ((size_t)(c.R + 2) * 2 + CONS2_THREADS / 32) *
-                             (c.w + 2 * HPAD) * sizeof(float);
+        const size_t bytes = (((size_t)(c.R + 2) * 2 + CONS2_THREADS / 32) *
+                                  (c.w + 2 * HPAD) + ((c.w + 3) & ~3) +
+                              (size_t)CONS2_THREADS * 4) * sizeof(float);
         if (bytes > smem) smem = bytes;
     }
     if (smem > 220 * 1024) return USL_ERR_UNSUPPORTED;
