@@ -20,9 +20,14 @@ term sums are all-reduced over NCCL inside the forward.
 `e2e`    : the same metric through the public API with HOST (pinned) inputs:
            every step copies its stereo pair and predictions to the device,
            runs the step eagerly and reads the two losses back.
-`roofline`: the dominant kernel, timed alone with CUDA events, algorithmic
-           bytes over its duration, against the measured
-           HBM peak of MEASURED_PEAKS.json.
+`roofline`: the dominant kernel -- the column-marching fused loss kernel, which
+           produces the loss sums AND the gradients in one pass (its four
+           per-scale launches run concurrently and are timed together, alone,
+           with CUDA events on the launching stream) -- algorithmic bytes of
+           loss forward + backward (127.5 B/pixel) over
+           its duration, against the measured HBM peak of MEASURED_PEAKS.json.
+           `achieved_onepass` is the same with the bytes a one-pass kernel must
+           really move (read 40 + write 16 B per scale-pixel = 74.4 B/pixel).
 `cpu_baseline`: the oracle port (same ATen op sequence as the reference's CPU
            path) on the host cores, bounded sample.
 """
@@ -320,17 +325,16 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_kind = measured_peak()
-    alg = {'pyramid': BYTES_PYR, 'loss_fwd': BYTES_FWD,
-           'loss_bwd_scatter': 0.0, 'loss_bwd_main': BYTES_BWD}
-    dom = max(('loss_fwd', 'loss_bwd_main', 'pyramid'),
-              key=lambda k: kern[k])
-    achieved = alg[dom] * pixels / (kern[dom] * 1e-3) / 1e9
+    # the fused column kernel does forward and backward of the loss in one pass
+    dom = 'loss_fused_main'
+    achieved = (BYTES_FWD + BYTES_BWD) * pixels / (kern[dom] * 1e-3) / 1e9
+    achieved_onepass = 56.0 * PYRAMID_FACTOR * pixels / (kern[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get(dom)
+                traffic = json.load(f).get('col_kernel_bytes_per_launch')
         except Exception:
             traffic = None
     cores = os.cpu_count() or 1
@@ -352,11 +356,20 @@ def run_ours(args, rank, world, local_rank):
         'eager_value': world * pixels / (ms_eager * 1e-3) / 1e6,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e},
-        'gpu_launches': 6 * args.steps,
+        # pyramid, 4 column kernels + scatter + reduce + combine in forward;
+        # 4 + 1 launches in backward (they return at once: unit upstream grads)
+        'gpu_launches': 13 * args.steps,
         'kernels_ms': kern,
-        'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved,
+        'roofline': {'bound': 'hbm',
+                     'kernel': 'col_kernel (fused loss fwd+bwd, 4 concurrent '
+                               'per-scale launches)',
+                     'achieved': achieved,
                      'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'peak_kind': peak_kind, 'traffic': traffic,
+                     'achieved_onepass': achieved_onepass,
+                     'ms': kern[dom],
+                     'note': 'issue/shared-memory bound, not HBM bound: see '
+                             'DESIGN.md section 5',
                      'step_frac': BYTES_STEP * pixels / (ms_step * 1e-3) / 1e9
                      / peak},
         'cpu_baseline': {'value': pixels / (cpu_ms * 1e-3) / 1e6,
@@ -413,7 +426,7 @@ def kernel_times(K, U, fn, sets, dev, reps):
         prepared[i % nsets][2], prepared[i % nsets][3], dev))
     out['loss_bwd_scatter'] = t(lambda i: K.loss_backward(
         prepared[i % nsets][2], prepared[i % nsets][4], one, one, dev, 1))
-    out['loss_bwd_main'] = t(lambda i: K.loss_backward(
+    out['loss_fused_main'] = t(lambda i: K.loss_backward(
         prepared[i % nsets][2], prepared[i % nsets][4], one, one, dev, 2))
     # the training step's path: sums + gradients in one pass (scatter kernel,
     # marching kernel in GRAD mode, reduce, combine)
@@ -421,9 +434,6 @@ def kernel_times(K, U, fn, sets, dev, reps):
         out['loss_onepass'] = t(lambda i: K.loss_forward(
             prepared[i % nsets][2], prepared[i % nsets][4], dev,
             with_grad=True))
-        out['loss_onepass_main'] = out['loss_onepass'] - \
-            out['loss_bwd_scatter'] - (out['loss_fwd'] - out['loss_fwd_main']
-                                       if 'loss_fwd_main' in out else 0.0)
     except Exception as e:      # not eligible for this workload
         out['loss_onepass'] = None
     return out

@@ -37,18 +37,21 @@ static void to_params(const UslLossConfig* cfg, const UslLossScale* s,
 template <class C, int PAR>
 static void step(const LossParams& P, const CGeo& G, const CRings& S, int r,
                  int r1, int ring_last, int nt, std::vector<CState>& T) {
-    if (C::MODE == MODE_PLAIN) {
-        const int row = S.RW[c_step_index(G, r)].issue;
-        if (row >= 0)
-            for (int l = 0; l < 32; ++l) c_ring_issue(P, G, S, C::SROW, row, l);
-    } else if (r + 2 <= ring_last) {
-        for (int t = 0; t < nt; ++t) c_ring_fill<C::SROW, C::MODE>(P, G, T[t], r + 2);
-    }
-    for (int t = 0; t < nt; ++t) c_p1<C>(P, G, S, r, T[t]);
+    // barrier | P2(r), V(r+1) | barrier | P3(r), ring request, P1(r+1)
     for (int t = 0; t < nt; ++t) c_p2<C, PAR>(P, G, S, r, T[t]);
-    for (int t = 0; t < nt; ++t) {
-        c_p3<C, PAR>(P, G, S, r, T[t]);
-        if (C::STEADY || r + 1 <= r1) c_pV<C::SROW, C::MODE, C::STEADY>(P, G, S, r, t, nt, T[t]);
+    if (C::STEADY || r + 1 <= r1)
+        for (int t = 0; t < nt; ++t)
+            c_pV<C::SROW, C::MODE, C::STEADY>(P, G, S, r, t, nt, T[t]);
+    for (int t = 0; t < nt; ++t) c_p3<C, PAR>(P, G, S, r, T[t]);
+    if (C::STEADY || r + 1 <= r1) {
+        if (C::MODE == MODE_PLAIN) {
+            const int row = S.RW[c_step_index(G, r + 1)].issue;
+            if (C::STEADY || row >= 0)
+                for (int l = 0; l < 32; ++l) c_ring_issue(P, G, S, C::SROW, row, l);
+        } else if (r + 3 <= ring_last) {
+            for (int t = 0; t < nt; ++t) c_ring_fill<C::SROW, C::MODE>(P, G, T[t], r + 3);
+        }
+        for (int t = 0; t < nt; ++t) c_p1<C>(P, G, S, r + 1, T[t]);
     }
 }
 
@@ -66,14 +69,15 @@ static void unit(const LossParams& P, const CGeo& G, int nt, int terms_ct,
     for (int t = 0; t < nt; ++t) c_init_unit<SROW, GRAD, MODE>(P, G, S, t, nt);
     const int r0 = c_first_row(G), r1 = c_last_row(G);
     const int ring_last = c_last_ring_row(P, G);
-    for (int row = r0 - 1; row <= r0 + 1 && row <= ring_last; ++row) {
+    for (int row = r0 - 1; row <= r0 + 2 && row <= ring_last; ++row) {
         if (MODE == MODE_PLAIN)
             for (int l = 0; l < 32; ++l) c_ring_issue(P, G, S, SROW, row, l);
         else for (int t = 0; t < nt; ++t) c_ring_fill<SROW, MODE>(P, G, T[t], row);
     }
     for (int t = 0; t < nt; ++t) c_pV<SROW, MODE, false>(P, G, S, r0 - 1, t, nt, T[t]);
+    for (int t = 0; t < nt; ++t) c_p1<Cfg<SROW, GRAD, MODE, -1, false>>(P, G, S, r0, T[t]);
     const int s_lo = G.ya + 2;
-    const int s_hi = (G.yb - 1 < P.h - 3) ? G.yb - 1 : P.h - 3;
+    const int s_hi = ((G.yb - 1 < P.h - 3) ? G.yb - 1 : P.h - 3) - 1;
     using CG = Cfg<SROW, GRAD, MODE, -1, false>;
     using CS = Cfg<SROW, GRAD, MODE, -1, true>;
     using HG = Cfg<SROW, GRAD, MODE, 47, false>;

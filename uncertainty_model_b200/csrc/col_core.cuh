@@ -158,14 +158,14 @@ USL_HD void mbar_wait(uint32_t, uint32_t) {}
 constexpr int SEG_PAD = 4;
 constexpr int NHIST_GRAD = 11;  // dI[3], y*dI[3], x*dI[3], l1, u
 constexpr int NHIST_FWD = 2;    // l1, u
-constexpr int NSLOT = 3;        // input ring depth (rows r-1 | r, r+1, r+2)
+constexpr int NSLOT = 4;        // input ring depth (rows r, r+1, r+2 | r+3 in flight)
 constexpr int NPL = 5;          // planes per ring slot: x[3], d, u
 enum {
     ROW_Y = 0,      // [3]  recon of the current row        (right neighbours read)
     ROW_DS = 3,     // [4]  ring of channel-summed dssim rows
     ROW_IN = 7,     // [NSLOT][NPL] own view(s): image, disparity, uncertainty rows
-    ROW_OPP = 22,   // [NSLOT][NPL] opposite view (one-view units): image, disparity
-    ROW_HS = 37,    // [3][NH] thread-private history of the rows in flight
+    ROW_OPP = 27,   // [NSLOT][NPL] opposite view (one-view units): image, disparity
+    ROW_HS = 47,    // [3][NH] thread-private history of the rows in flight
 };
 USL_HD constexpr int row_gx(bool grad) {     // [9] G(q) of the current window row
     return ROW_HS + 3 * (grad ? NHIST_GRAD : NHIST_FWD);

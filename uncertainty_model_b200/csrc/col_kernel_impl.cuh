@@ -20,26 +20,32 @@ struct ColArgs {
     int skip_if_unit;
 };
 
+// One step, entered with P1(r) done and its barrier still to come:
+//   barrier | P2(r), V(r+1) | barrier | P3(r), ring request, P1(r+1)
+// P3(r) and P1(r+1) share an interval: what P1 writes is either private to the
+// thread (history, registers) or read only after the next barrier.
 template <class C, int PAR>
 __device__ __forceinline__ void col_step(const LossParams& P, const CGeo& G,
                                          const CRings& S, int r, int r_last,
                                          int ring_last, CState& T) {
-    if (C::MODE == MODE_PLAIN) {
-        if (threadIdx.x < 32) {
-            const int row = S.RW[c_step_index(G, r)].issue;
-            if (row >= 0) c_ring_issue(P, G, S, C::SROW, row, threadIdx.x);
-        }
-    } else if (r + 2 <= ring_last) {
-        c_ring_fill<C::SROW, C::MODE>(P, G, T, r + 2);
-    }
-    c_p1<C>(P, G, S, r, T);
     __syncthreads();
     c_p2<C, PAR>(P, G, S, r, T);
-    __syncthreads();
-    c_p3<C, PAR>(P, G, S, r, T);
     if (C::STEADY || r + 1 <= r_last)
         c_pV<C::SROW, C::MODE, C::STEADY>(P, G, S, r, threadIdx.x, blockDim.x, T);
     __syncthreads();
+    c_p3<C, PAR>(P, G, S, r, T);
+    if (C::STEADY || r + 1 <= r_last) {
+        // row r+3 replaces row r in the ring (its last readers were P2 / V above)
+        if (C::MODE == MODE_PLAIN) {
+            if (threadIdx.x < 32) {
+                const int row = S.RW[c_step_index(G, r + 1)].issue;
+                if (C::STEADY || row >= 0) c_ring_issue(P, G, S, C::SROW, row, threadIdx.x);
+            }
+        } else if (r + 3 <= ring_last) {
+            c_ring_fill<C::SROW, C::MODE>(P, G, T, r + 3);
+        }
+        c_p1<C>(P, G, S, r + 1, T);
+    }
 }
 
 template <int SROW, bool GRAD, int MODE, int TERMS>
@@ -85,18 +91,20 @@ col_kernel(const __grid_constant__ ColArgs A) {
     // the ring starts one row above the first step: V(r0) may sample it
     if (MODE == MODE_PLAIN) {
         if (tid < 32)
-            for (int row = r0 - 1; row <= r0 + 1 && row <= ring_last; ++row)
+            for (int row = r0 - 1; row <= r0 + 2 && row <= ring_last; ++row)
                 c_ring_issue(P, G, S, SROW, row, tid);
     } else {
-        for (int row = r0 - 1; row <= r0 + 1 && row <= ring_last; ++row)
+        for (int row = r0 - 1; row <= r0 + 2 && row <= ring_last; ++row)
             c_ring_fill<SROW, MODE>(P, G, T, row);
         __syncthreads();
     }
     c_pV<SROW, MODE, false>(P, G, S, r0 - 1, tid, blockDim.x, T);
     __syncthreads();
+    c_p1<CG>(P, G, S, r0, T);
     // r0 = ya - 2 is even (strip heights are even): PAR is the row parity.
-    // Interior steps (see Cfg::STEADY) run the specialised body.
-    const int s_lo = G.ya + 2, s_hi = min(G.yb - 1, P.h - 3);
+    // Interior steps (see Cfg::STEADY; the step also runs P1 of the row after)
+    // use the specialised body.
+    const int s_lo = G.ya + 2, s_hi = min(G.yb - 1, P.h - 3) - 1;
     int r = r0;
     for (; r < s_lo && r <= r1; r += 2) {
         col_step<CG, 0>(P, G, S, r, r1, ring_last, T);

@@ -41,12 +41,14 @@ bool col_eligible(const UslLossConfig* cfgs, const UslLossScale* scales, int n) 
 
 int col_plan(ColPlan* M, bool grad) {
     const int maxT = COL_MAX_THREADS;
-    const int R0 = env_int3("USL_COL_R0", 32), R1 = env_int3("USL_COL_R", 16);
+    // widest two-view unit (in threads): wider rows get one unit per view
+    const int maxT2 = env_int3("USL_COL_MAXT2", COL_MAX_THREADS);
+    const int R0 = env_int3("USL_COL_R0", 64), R1 = env_int3("USL_COL_R", 16);
     long long rows = 0;
     for (int i = 0; i < M->n; ++i) {
         LossParams& p = M->P[i];
         int nv, tiles = 1, TW = p.w, LW = p.w;
-        if (2 * p.w <= maxT) nv = 2;
+        if (2 * p.w <= maxT2) nv = 2;
         else if (p.w <= maxT) nv = 1;
         else {
             nv = 1;
