@@ -405,12 +405,16 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
         const int col = k < VPAD ? k : P.w + k;
         st_f4(S.V + (size_t)vi * (P.w + 2 * VPAD) + col, 0.f, 0.f, 0.f, 0.f);
     }
-    const int segw = G.nv * (G.LW + 2 * SEG_PAD);
-    for (int i = tid; i < n_rows(GRAD) * segw; i += nt) {
-        const int row = i / segw, k = i - row * segw;
-        S.rows[(size_t)row * SROW + k] = 0.f;
+    // the pads of every row ([4 | LW | 4] per view segment) must read as zero;
+    // everything between them is written before it is read
+    const int npad = G.nv * 2 * SEG_PAD;
+    for (int i = tid; i < n_rows(GRAD) * npad; i += nt) {
+        const int row = i / npad, k = i - row * npad;
+        const int vi = k / (2 * SEG_PAD), j = k - vi * 2 * SEG_PAD;
+        const int col = vi * (G.LW + 2 * SEG_PAD) + (j < SEG_PAD ? j : G.LW + j);
+        S.rows[(size_t)row * SROW + col] = 0.f;
     }
-    // the zeros above were generic stores into rows the bulk copies will fill
+    // (generic stores next to the rows the bulk copies will fill)
     if (MODE == MODE_PLAIN) fence_proxy_async();
     if (MODE == MODE_PLAIN && tid == 0) {
         for (int s = 0; s < NSLOT; ++s) mbar_init(S.mbar + s, 1);

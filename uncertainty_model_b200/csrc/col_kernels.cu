@@ -107,38 +107,8 @@ int col_launch_scale(const ColPlan* M, int i, bool grad, int skip_if_unit,
     return USL_ERR_UNSUPPORTED;
 }
 
-// Side streams for the concurrent per-scale launches: one small pool per host
-// thread and device, created on first use and never destroyed (immutable
-// afterwards; nothing is shared between host threads).
-namespace {
-constexpr int POOL_SIDE = USL_MAX_SCALES - 1;
-struct StreamPool {
-    bool ready = false, failed = false;
-    cudaStream_t side[POOL_SIDE];
-    cudaEvent_t fork, join[POOL_SIDE];
-};
-StreamPool* pool_for_current_device() {
-    constexpr int MAX_DEV = 64;
-    thread_local StreamPool pools[MAX_DEV];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
-    StreamPool& p = pools[dev];
-    if (p.failed) return nullptr;
-    if (!p.ready) {
-        bool ok = cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int i = 0; ok && i < POOL_SIDE; ++i)
-            ok = cudaStreamCreateWithFlags(&p.side[i], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) { p.failed = true; cudaGetLastError(); return nullptr; }
-        p.ready = true;
-    }
-    return &p;
-}
-}  // namespace
-
 int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st) {
-    StreamPool* pool = (M->n > 1 && !getenv("USL_COL_SERIAL"))
-                           ? pool_for_current_device() : nullptr;
+    StreamPool* pool = (M->n > 1 && !getenv("USL_COL_SERIAL")) ? stream_pool() : nullptr;
     if (!pool) {
         for (int i = 0; i < M->n; ++i) {
             const int rc = col_launch_scale(M, i, grad, skip_if_unit, st);
@@ -149,7 +119,8 @@ int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st) {
     // fork: what precedes on `st` (the scatter kernel) is ordered before every
     // scale; scale 0 stays on `st` and is launched first
     if (cudaEventRecord(pool->fork, st) != cudaSuccess) return USL_ERR_CUDA;
-    int rc = col_launch_scale(M, 0, grad, skip_if_unit, st);
+    const bool small_first = getenv("USL_COL_SMALL_FIRST") != nullptr;
+    int rc = small_first ? USL_OK : col_launch_scale(M, 0, grad, skip_if_unit, st);
     for (int i = 1; i < M->n && rc == USL_OK; ++i) {
         cudaStream_t s = pool->side[i - 1];
         if (cudaStreamWaitEvent(s, pool->fork, 0) != cudaSuccess) { rc = USL_ERR_CUDA; break; }
@@ -159,6 +130,7 @@ int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st) {
             cudaStreamWaitEvent(st, pool->join[i - 1], 0) != cudaSuccess)
             rc = rc == USL_OK ? USL_ERR_CUDA : rc;
     }
+    if (small_first && rc == USL_OK) rc = col_launch_scale(M, 0, grad, skip_if_unit, st);
     return rc;
 }
 

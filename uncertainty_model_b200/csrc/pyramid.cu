@@ -3,13 +3,16 @@
 // Every level is resampled from the full-resolution stereo pair with
 // align_corners=True bilinear taps; level 0 is the input itself and is
 // aliased by the host, never copied.  All levels >= 1 are produced by one
-// launch: the flat output index space of the levels is concatenated and a
-// grid-stride loop walks it, so the full-resolution rows a CTA touches for
-// level 1 are the same rows (hot in L1/L2) its neighbours touch for levels 2
-// and 3.  HBM-bound: 24 B read + 7.875 B written per full-resolution pixel.
+// launch, largest level first: a CTA owns a tile of consecutive output rows of
+// one (level, sample, channel) plane, a thread one output column of one of
+// those rows, so the only integer divisions are two 32-bit ones per thread and
+// the four taps of a warp read two contiguous runs of the source rows.
+// HBM-bound: 24 B read + 7.875 B written per full-resolution pixel.
 #include "usl_common.cuh"
 
 namespace usl {
+
+constexpr int PYR_THREADS = 256;
 
 struct PyramidParams {
     const float* src;
@@ -19,26 +22,29 @@ struct PyramidParams {
     float* dst[USL_MAX_SCALES];
     int h[USL_MAX_SCALES], w[USL_MAX_SCALES];
     float sy[USL_MAX_SCALES], sx[USL_MAX_SCALES];
-    long long start[USL_MAX_SCALES + 1];   // prefix of per-level element counts
+    int rows[USL_MAX_SCALES];      // output rows per CTA
+    int tiles[USL_MAX_SCALES];     // CTAs per plane
+    int cta_start[USL_MAX_SCALES + 1];
 };
 
-__global__ void __launch_bounds__(256)
-pyramid_kernel(const PyramidParams p) {
-    const long long total = p.start[p.levels];
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-         i < total; i += stride) {
-        int l = 0;
-        while (l + 1 < p.levels && i >= p.start[l + 1]) ++l;
-        long long r = i - p.start[l];
-        const int w = p.w[l], h = p.h[l];
-        const int x = (int)(r % w); r /= w;
-        const int y = (int)(r % h); r /= h;
-        const int c = (int)(r % p.C);
-        const int b = (int)(r / p.C);
+__global__ void __launch_bounds__(PYR_THREADS)
+pyramid_kernel(const __grid_constant__ PyramidParams p) {
+    int l = 0;
+    while (l + 1 < p.levels && (int)blockIdx.x >= p.cta_start[l + 1]) ++l;
+    const int local = blockIdx.x - p.cta_start[l];
+    const int plane_i = local / p.tiles[l];
+    const int tile = local - plane_i * p.tiles[l];
+    const int b = plane_i / p.C, c = plane_i - b * p.C;
+    const int w = p.w[l], h = p.h[l];
+    const float* s = p.src + b * p.src_bs + c * p.src_cs;
+    float* d = p.dst[l] + (long long)plane_i * h * w;
+    const int y0 = tile * p.rows[l];
+    if (w <= PYR_THREADS) {
+        const int ry = threadIdx.x / w, x = threadIdx.x - ry * w;
+        const int y = y0 + ry;
+        if (ry >= p.rows[l] || y >= h) return;
         const TapAC ty = ac_taps(y, p.sy[l], p.H);
         const TapAC tx = ac_taps(x, p.sx[l], p.W);
-        const float* s = p.src + b * p.src_bs + c * p.src_cs;
         const float* r0 = s + (long long)ty.i0 * p.W;
         const float* r1 = s + (long long)ty.i1 * p.W;
         const float v00 = __ldg(r0 + tx.i0), v01 = __ldg(r0 + tx.i1);
@@ -46,7 +52,20 @@ pyramid_kernel(const PyramidParams p) {
         // ATen: w0y * (w0x * v00 + w1x * v01) + w1y * (w0x * v10 + w1x * v11)
         const float top = tx.w0 * v00 + tx.w1 * v01;
         const float bot = tx.w0 * v10 + tx.w1 * v11;
-        p.dst[l][i - p.start[l]] = ty.w0 * top + ty.w1 * bot;
+        d[(long long)y * w + x] = ty.w0 * top + ty.w1 * bot;
+    } else {
+        if (y0 >= h) return;
+        const TapAC ty = ac_taps(y0, p.sy[l], p.H);
+        const float* r0 = s + (long long)ty.i0 * p.W;
+        const float* r1 = s + (long long)ty.i1 * p.W;
+        for (int x = threadIdx.x; x < w; x += PYR_THREADS) {
+            const TapAC tx = ac_taps(x, p.sx[l], p.W);
+            const float v00 = __ldg(r0 + tx.i0), v01 = __ldg(r0 + tx.i1);
+            const float v10 = __ldg(r1 + tx.i0), v11 = __ldg(r1 + tx.i1);
+            const float top = tx.w0 * v00 + tx.w1 * v01;
+            const float bot = tx.w0 * v10 + tx.w1 * v11;
+            d[(long long)y0 * w + x] = ty.w0 * top + ty.w1 * bot;
+        }
     }
 }
 
@@ -64,7 +83,7 @@ extern "C" int usl_pyramid(const float* src, int B, int C, int H, int W,
     p.src = src; p.src_bs = src_bs; p.src_cs = src_cs;
     p.B = B; p.C = C; p.H = H; p.W = W;
     p.levels = scales - 1;
-    p.start[0] = 0;
+    p.cta_start[0] = 0;
     for (int l = 0; l < p.levels; ++l) {
         const int h = H >> (l + 1), w = W >> (l + 1);
         if (h < 1 || w < 1 || !dst[l + 1]) return USL_ERR_ARG;
@@ -72,12 +91,13 @@ extern "C" int usl_pyramid(const float* src, int B, int C, int H, int W,
         p.h[l] = h; p.w[l] = w;
         p.sy[l] = ac_scale(H, h);
         p.sx[l] = ac_scale(W, w);
-        p.start[l + 1] = p.start[l] + (long long)B * C * h * w;
+        p.rows[l] = w <= PYR_THREADS ? PYR_THREADS / w : 1;
+        p.tiles[l] = (h + p.rows[l] - 1) / p.rows[l];
+        const long long ctas = (long long)B * C * p.tiles[l];
+        if (p.cta_start[l] + ctas > 0x7fffffffLL) return USL_ERR_UNSUPPORTED;
+        p.cta_start[l + 1] = p.cta_start[l] + (int)ctas;
     }
-    const long long total = p.start[p.levels];
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    pyramid_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    pyramid_kernel<<<(unsigned)p.cta_start[p.levels], PYR_THREADS, 0,
+                     (cudaStream_t)stream>>>(p);
     return check_launch();
 }

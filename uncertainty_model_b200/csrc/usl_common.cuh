@@ -27,6 +27,35 @@ inline int num_sms() {
     return cached;
 }
 
+// Side streams for launches that may run concurrently with what is on the
+// caller's stream: one small pool per host thread and device, created on first
+// use and never destroyed (immutable afterwards; nothing is shared between
+// host threads).  side[0 .. USL_MAX_SCALES-2]: per-scale launches of the fused
+// kernel; side[USL_MAX_SCALES-1]: the scatter kernel.
+struct StreamPool {
+    bool ready = false, failed = false;
+    cudaStream_t side[USL_MAX_SCALES];
+    cudaEvent_t fork, fork2, join[USL_MAX_SCALES];
+};
+inline StreamPool* stream_pool() {
+    constexpr int MAX_DEV = 64;
+    thread_local StreamPool pools[MAX_DEV];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    StreamPool& p = pools[dev];
+    if (p.failed) return nullptr;
+    if (!p.ready) {
+        bool ok = cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&p.fork2, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < USL_MAX_SCALES; ++i)
+            ok = cudaStreamCreateWithFlags(&p.side[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { p.failed = true; cudaGetLastError(); return nullptr; }
+        p.ready = true;
+    }
+    return &p;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
