@@ -43,7 +43,11 @@ int col_plan(ColPlan* M, bool grad) {
     const int maxT = COL_MAX_THREADS;
     // widest two-view unit (in threads): wider rows get one unit per view
     const int maxT2 = env_int3("USL_COL_MAXT2", COL_MAX_THREADS);
-    const int R0 = env_int3("USL_COL_R0", 64), R1 = env_int3("USL_COL_R", 16);
+    // Strip heights.  The CTAs of the largest scale are long and hold a whole
+    // SM each (registers); the other scales run beside them only on the SMs
+    // they leave free.  Measured best (profiles/, config 2): the largest scale
+    // on ~2/3 of the SMs in ONE wave, 32-row strips below.
+    const int R0 = env_int3("USL_COL_R0", 0), R1 = env_int3("USL_COL_R", 32);
     long long rows = 0;
     for (int i = 0; i < M->n; ++i) {
         LossParams& p = M->P[i];
@@ -60,6 +64,14 @@ int col_plan(ColPlan* M, bool grad) {
         // strip height: long strips for the big scale (less halo work), short
         // ones for the small scales (they fill the tail of the step)
         int wantR = (i == 0) ? R0 : R1;
+        if (i == 0 && R0 == 0) {
+            const int per_strip = tiles * p.B * (2 / nv);
+            int want_strips = (7 * num_sms() / 10) / per_strip;
+            if (want_strips < 1) want_strips = 1;
+            wantR = (p.h + want_strips - 1) / want_strips;
+            if (wantR < 32) wantR = 32;
+            if (wantR > 128) wantR = 128;       // (per-step tables live in shared memory)
+        }
         int strips = (p.h + wantR - 1) / wantR;
         int R = (((p.h + strips - 1) / strips) + 1) & ~1;
         strips = (p.h + R - 1) / R;
@@ -98,6 +110,9 @@ extern template int col_launch_class<64>(const ColPlan*, int, bool, int, cudaStr
 
 int col_launch_scale(const ColPlan* M, int i, bool grad, int skip_if_unit,
                      cudaStream_t st) {
+    // (profiling aid: USL_COL_ONLY = bit mask of the scales to launch)
+    static const int only = env_int3("USL_COL_ONLY", 0xff);
+    if (!((only >> i) & 1)) return USL_OK;
     switch (M->cls[i]) {
         case 512: return col_launch_class<512>(M, i, grad, skip_if_unit, st);
         case 256: return col_launch_class<256>(M, i, grad, skip_if_unit, st);
