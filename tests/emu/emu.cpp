@@ -77,7 +77,8 @@ extern "C" int emu_loss_fwd(const UslLossConfig* cfg, const UslLossScale* s,
     return 0;
 }
 
-static void run_scatter(const LossParams& P, int consR, const float* gout) {
+static void run_scatter(const LossParams& P, int consR, const float* gout,
+                        int accumulate = 0) {
     ConsParams C = {};
     C.B = P.B; C.h = P.h; C.w = P.w;
     C.disp = P.disp; C.d_bs = P.d_bs; C.d_cs = P.d_cs;
@@ -87,6 +88,7 @@ static void run_scatter(const LossParams& P, int consR, const float* gout) {
     C.terms = P.terms & (TERM_CONS_D | TERM_CONS_U);
     C.coef_dd = P.coef[ACC_CONS_D]; C.coef_ud = P.coef[ACC_CONS_U];
     C.R = consR > C.h ? C.h : consR;
+    C.accumulate = accumulate;
     std::vector<float> arena(cons_ring_floats(C.w));
     for (int b = 0; b < C.B; ++b)
         for (int ya = 0; ya < C.h; ya += C.R) {
@@ -110,6 +112,15 @@ extern "C" int emu_cons_scatter(const UslLossConfig* cfg, const UslLossScale* s,
     LossParams P;
     to_params(cfg, s, 16, 16, &P);
     if (P.terms & (TERM_CONS_D | TERM_CONS_U)) run_scatter(P, consR, gout);
+    return 0;
+}
+
+// ... added to what the column-marching emulation stored before.
+extern "C" int emu_cons_scatter_add(const UslLossConfig* cfg, const UslLossScale* s,
+                                    int consR, const float* gout) {
+    LossParams P;
+    to_params(cfg, s, 16, 16, &P);
+    if (P.terms & (TERM_CONS_D | TERM_CONS_U)) run_scatter(P, consR, gout, 1);
     return 0;
 }
 

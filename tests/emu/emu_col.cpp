@@ -140,7 +140,8 @@ static int run(const UslLossConfig* cfg, const UslLossScale* s, int maxT,
                     const bool al = (P.w % 4 == 0) &&
                         ((((uintptr_t)P.img | (uintptr_t)P.disp | (uintptr_t)P.unc) & 15) == 0) &&
                         (((P.img_bs | P.img_cs | P.d_bs | P.d_cs | P.u_bs | P.u_cs) & 3) == 0);
-                    const int hot = ((int)P.terms == 47 && !tiled && !(n & 31) && al && !P.grad_recon_in) ? 47 : -1;
+                    const int hot = ((int)P.terms == 47 && !tiled && !(n & 31) && al && !P.grad_recon_in &&
+                                     !P.err_out && !P.recon_out) ? 47 : -1;
                     if (tiled) unit<GRAD, MODE_TILED>(P, G, nt, -1, sums);
                     else if ((n & 31) || !al) unit<GRAD, MODE_MASKED>(P, G, nt, -1, sums);
                     else unit<GRAD, MODE_PLAIN>(P, G, nt, hot, sums);

@@ -43,6 +43,8 @@ def emu():
         lib.emu_cons_scatter.argtypes = [C.POINTER(UslLossConfig),
                                          C.POINTER(UslLossScale), C.c_int,
                                          C.POINTER(C.c_float)]
+        lib.emu_cons_scatter_add.restype = C.c_int
+        lib.emu_cons_scatter_add.argtypes = lib.emu_cons_scatter.argtypes
         lib.emu_loss_bwd.restype = C.c_int
         lib.emu_loss_bwd.argtypes = [C.POINTER(UslLossConfig),
                                      C.POINTER(UslLossScale), C.c_int, C.c_int,
@@ -181,7 +183,7 @@ def emu_col_scale(settings: LossSettings, terms, coefs, images, pred, *,
                   g=(1.0, 1.0), maxT=512, R=16, consR=16, want_recon=False,
                   grad_recon_in=None):
     """The column-marching kernels (forward-only mode, then the one-pass
-    sums+gradient mode on top of the emulated scatter) for ONE scale.
+    sums+gradient mode, then the emulated scatter on top) for ONE scale.
 
     Returns dict(sums, sums_grad, err, recon, grad_pred)."""
     L = emu_col()
@@ -200,12 +202,10 @@ def emu_col_scale(settings: LossSettings, terms, coefs, images, pred, *,
                     grad_recon_in=grad_recon_in, grad_disp=grad_pred[:, 0:2],
                     grad_unc=grad_pred[:, 2:4])
     gout = (C.c_float * 2)(*g)
-    acc = 0
-    if terms & 34:          # TERM_CONS_D | TERM_CONS_U
-        emu().emu_cons_scatter(C.byref(cfg), C.byref(sc), consR, gout)
-        acc = 1
     sums_g = (C.c_double * 6)()
-    assert L.emu_col_grad(C.byref(cfg), C.byref(sc), maxT, R, acc, gout,
+    assert L.emu_col_grad(C.byref(cfg), C.byref(sc), maxT, R, 0, gout,
                           sums_g) == 0
+    if terms & 34:          # TERM_CONS_D | TERM_CONS_U: the scatter adds its part
+        emu().emu_cons_scatter_add(C.byref(cfg), C.byref(sc), consR, gout)
     return dict(sums=list(sums), sums_grad=list(sums_g), err=err_out,
                 recon=recon_out, grad_pred=grad_pred)

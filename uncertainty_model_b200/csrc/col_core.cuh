@@ -207,8 +207,8 @@ struct alignas(16) RowV {    // vertical taps of the warp for row r + 1
     float w0, w1;            // weights (zero for rows outside the image)
 };
 struct alignas(16) RowW {    // ring synchronisation of the step
-    int wait_cur;            // slot | parity << 8 of row r            (-1: none)
-    int wait_v0, wait_v1;    // ... of the two source rows of V(r + 1) (-1: none)
+    unsigned wait_cur;       // wait word (c_wait_word) of row r             (0: none)
+    unsigned wait_v0, wait_v1;   // ... of the two source rows of V(r + 1)   (0: none)
     int issue;               // row to request at the start of the step (-1: none)
 };
 
@@ -260,6 +260,7 @@ struct CState {
     float x[3], d, u;        // own inputs, row r
     float xp[3], dp, up;     // row r-1
     float y[3];              // recon of row r                    (P1 -> P2)
+    float g[9];              // own G(q = r-2)                    (P2 -> P3)
     float H[2][3][4];        // horizontal 3-sums of the two previous rows
     float HG[2][3][3];       // ... of G of the two previous window rows
     float gd[3], gu[3];      // gradient accumulators of rows r, r-1, r-2
@@ -276,7 +277,8 @@ struct CState {
     int ax0, ax1;            // column offsets (from the own column) of the up-sample taps
     unsigned o_img, o_d, o_u;   // element offsets of (b, own view, row 0, c)
     unsigned o_oi, o_od;        // ... of (b, opposite view, row 0, c): img, disp
-    float* p_gd; float* p_gu;   // gradient outputs at (b, own view, row ya, c)
+    unsigned o_gd, o_gu;        // element offsets of the gradient outputs: (b, own view,
+                                // next row to be finalised, c)
     int v, vi, c, lc;
     bool active, win_ok, has1;
 };
@@ -307,6 +309,7 @@ USL_HD void c_thread_init(const LossParams& P, const CGeo& G, const CRings& S,
     for (int a = 0; a < 3; ++a) T.gd[a] = T.gu[a] = 0.f;
     for (int k = 0; k < NUM_ACC; ++k) T.acc[k] = 0.f;
     for (int c = 0; c < 3; ++c) T.x[c] = T.xp[c] = T.y[c] = 0.f;
+    for (int k = 0; k < 9; ++k) T.g[k] = 0.f;
     T.d = T.dp = 0.f;
     T.u = T.up = 1.f;
     T.xbase = linspace01(T.c, w);
@@ -324,10 +327,10 @@ USL_HD void c_thread_init(const LossParams& P, const CGeo& G, const CRings& S,
     T.o_d = (unsigned)((long long)G.b * P.d_bs + (long long)T.v * P.d_cs + T.c);
     T.o_od = (unsigned)((long long)G.b * P.d_bs + (long long)(1 - T.v) * P.d_cs + T.c);
     T.o_u = (unsigned)((long long)G.b * P.u_bs + (long long)T.v * P.u_cs + T.c);
-    T.p_gd = P.grad_disp ? P.grad_disp + ((long long)G.b * P.gd_bs + (long long)T.v * P.gd_cs +
-                                          (long long)G.ya * w + T.c) : nullptr;
-    T.p_gu = P.grad_unc ? P.grad_unc + ((long long)G.b * P.gu_bs + (long long)T.v * P.gu_cs +
-                                        (long long)G.ya * w + T.c) : nullptr;
+    T.o_gd = (unsigned)((long long)G.b * P.gd_bs + (long long)T.v * P.gd_cs +
+                        (long long)G.ya * w + T.c);
+    T.o_gu = (unsigned)((long long)G.b * P.gu_bs + (long long)T.v * P.gu_cs +
+                        (long long)G.ya * w + T.c);
     T.txw = 0.f; T.axw = 0.f; T.ax0 = T.ax1 = 0;
     if (!T.active) return;
     const TapAC ax = ac_taps(T.c, G.sW, w - 2);
@@ -338,6 +341,16 @@ USL_HD void c_thread_init(const LossParams& P, const CGeo& G, const CRings& S,
     T.axw = ax.w1;
     if (GRAD && T.c <= w - 3)
         T.txw = upsample_transpose_weight(T.c, w - 2, w, G.sW);
+}
+
+// `w`: mbarrier shared-window address | parity << 31 (see c_wait_word), < 0 as
+// int only when the parity bit is set, so "no wait" is the value 0.
+template <bool SURE>
+USL_HD void c_ring_wait(unsigned w) {
+    if (SURE || w != 0u) mbar_wait(w & 0x7fffffffu, w >> 31);
+}
+USL_HD unsigned c_wait_word(const CRings& S, int slot, int parity) {
+    return (S.mbar_a + 8u * (unsigned)slot) | ((unsigned)parity << 31) | 0u;
 }
 
 // last image row the unit ever reads (own rows to yb+1, warp sources one more)
@@ -379,7 +392,7 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
         RowV v;
         RowW ww;
         v.o0 = v.o1 = 0; v.w0 = v.w1 = 0.f;
-        ww.wait_cur = ww.wait_v0 = ww.wait_v1 = ww.issue = -1;
+        ww.wait_cur = ww.wait_v0 = ww.wait_v1 = 0u; ww.issue = -1;
         const int rn = r + 1;
         if (rn >= 0 && rn < P.h) {
             const Tap2 ty = warp_row_taps(rn, P.h);
@@ -391,12 +404,12 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
             const int i1 = ok1 ? ty.i0 + 1 : ty.i0;
             v.o0 = c_ring_slot(G, i0) * NPL * SROW;
             v.o1 = c_ring_slot(G, i1) * NPL * SROW;
-            ww.wait_v0 = c_ring_slot(G, i0) | (c_ring_parity(G, i0) << 8);
-            ww.wait_v1 = c_ring_slot(G, i1) | (c_ring_parity(G, i1) << 8);
+            ww.wait_v0 = c_wait_word(S, c_ring_slot(G, i0), c_ring_parity(G, i0));
+            ww.wait_v1 = c_wait_word(S, c_ring_slot(G, i1), c_ring_parity(G, i1));
         }
         S.RV[i] = v;
         if (r >= 0 && r < P.h)
-            ww.wait_cur = c_ring_slot(G, r) | (c_ring_parity(G, r) << 8);
+            ww.wait_cur = c_wait_word(S, c_ring_slot(G, r), c_ring_parity(G, r));
         if (r + 2 >= G.ya && r + 2 <= last) ww.issue = r + 2;
         S.RW[i] = ww;
     }
@@ -506,12 +519,6 @@ USL_HD void c_ring_fill(const LossParams& P, const CGeo& G, const CState& T, int
 }
 
 // `sure`: the row is known to exist (no test of the table entry)
-template <bool SURE>
-USL_HD void c_ring_wait(const CRings& S, int slot_parity) {
-    if (SURE || slot_parity >= 0)
-        mbar_wait(S.mbar_a + 8u * (unsigned)(slot_parity & 0xff), (unsigned)(slot_parity >> 8));
-}
-
 // ---- V(r+1): vertical blend of the opposite view, whole row -------------------
 // Full-row units: thread (vi, lc) blends its own column from the ring.
 // Column-tiled units: the threads of the unit sweep the whole row from global.
@@ -525,8 +532,8 @@ USL_HD void c_pV(const LossParams& P, const CGeo& G, const CRings& S, int r,
     if (MODE != MODE_TILED) {
         if (MODE == MODE_PLAIN) {
             const RowW ww = S.RW[i];
-            c_ring_wait<STEADY>(S, ww.wait_v0);
-            c_ring_wait<STEADY>(S, ww.wait_v1);
+            c_ring_wait<STEADY>(ww.wait_v0);
+            c_ring_wait<STEADY>(ww.wait_v1);
         }
         if (MODE == MODE_MASKED && !T.active) return;
         const float* a = T.ob + t.o0;
@@ -592,7 +599,7 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
     T.dp = T.d; T.up = T.u;
     if (!STEADY && (r < 0 || r >= P.h)) return;
     const int i = c_step_index(G, r);
-    if (C::MODE == MODE_PLAIN) c_ring_wait<STEADY>(S, S.RW[i].wait_cur);
+    if (C::MODE == MODE_PLAIN) c_ring_wait<STEADY>(S.RW[i].wait_cur);
     if (MASKED && !T.active) return;
     const RowU ru = S.RU[i];
     const int nh = GRAD ? NHIST_GRAD : NHIST_FWD;
@@ -641,7 +648,7 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
     }
     hs[(nh - 2) * SROW] = l1;
     hs[(nh - 1) * SROW] = T.u;
-    if (!GRAD && P.recon_out && own_row && own != 0.f) {
+    if (!GRAD && C::TERMS < 0 && P.recon_out && own_row && own != 0.f) {
         const long long hwp = (long long)P.h * P.w;
         for (int c = 0; c < 3; ++c)
             P.recon_out[((long long)G.b * 6 + T.v * 3 + c) * hwp +
@@ -802,9 +809,12 @@ USL_HD void c_p2(const LossParams& P, const CGeo& G, const CRings& S, int r,
                 const float t1 = (2.0f * mx) * (n2 - n1);
                 const float t2 = (2.0f * my) * (ssim * (d2 - d1));
                 float* gx = T.sb + (row_gx(true) + c * 3) * SROW;
-                gx[0] = gb * ((t1 - t2) * inv);
-                gx[SROW] = (-2.0f * gb) * (ssim * (inv * d1));   // (2 y) dssim/dQ: the 2
-                gx[2 * SROW] = gb * (2.0f * (n1 * inv));
+                T.g[c * 3 + 0] = gb * ((t1 - t2) * inv);
+                T.g[c * 3 + 1] = (-2.0f * gb) * (ssim * (inv * d1));   // (2 y) dssim/dQ: the 2
+                T.g[c * 3 + 2] = gb * (2.0f * (n1 * inv));
+                gx[0] = T.g[c * 3 + 0];
+                gx[SROW] = T.g[c * 3 + 1];
+                gx[2 * SROW] = T.g[c * 3 + 2];
             }
         }
         T.sb[ru.ds_w] = dsum;
@@ -841,7 +851,7 @@ USL_HD void c_p3(const LossParams& P, const CGeo& G, const CRings& S, int r,
         if (q_ok) {
             for (int k = 0; k < 9; ++k) {
                 const float* g = T.sb + (row_gx(true) + k) * SROW;
-                hg[k] = (g[-2] + g[-1]) + g[0];          // windows c-2, c-1, c
+                hg[k] = (g[-2] + g[-1]) + T.g[k];        // windows c-2, c-1, c
             }
         } else {
             for (int k = 0; k < 9; ++k) hg[k] = 0.f;
@@ -895,16 +905,15 @@ USL_HD void c_p3(const LossParams& P, const CGeo& G, const CRings& S, int r,
             if (GRAD) gur = (G.ge_up * P.coef[ACC_UNC]) * (eu + 1.0f);
         }
     }
-    if (P.err_out)
+    if (C::TERMS < 0 && P.err_out)     // (optional outputs: generic variant only)
         P.err_out[((long long)G.b * 2 + T.v) * ((long long)P.h * P.w) + ro + T.c] = e;
     if (GRAD) {
-        // rows are finalised in order: the output pointers walk down with them
-        float a = T.gd[2];
-        if (P.grad_disp_accumulate) a += *T.p_gd;
-        *T.p_gd = a;
-        *T.p_gu = T.gu[2] + gur;
-        T.p_gd += P.w;
-        T.p_gu += P.w;
+        // rows are finalised in order: the output offsets walk down with them.
+        // Pure stores: the scatter kernel adds its part afterwards.
+        P.grad_disp[T.o_gd] = T.gd[2];
+        P.grad_unc[T.o_gu] = T.gu[2] + gur;
+        T.o_gd += (unsigned)P.w;
+        T.o_gu += (unsigned)P.w;
     }
 }
 

@@ -157,7 +157,9 @@ int col_launch_class(const ColPlan* M, int i, bool grad, int skip_if_unit,
     A.skip_if_unit = skip_if_unit;
     const int grid = M->units[i], nt = M->threads[i], mode = M->mode[i];
     const size_t smem = M->smem[i];
-    const bool hot = (A.P.terms == COL_HOT_TERMS) && !A.P.grad_recon_in;
+    // the hot variant has no optional inputs / outputs compiled in
+    const bool hot = (A.P.terms == COL_HOT_TERMS) && !A.P.grad_recon_in &&
+                     !A.P.err_out && !A.P.recon_out;
 #define USL_COL_GO(GRAD, MODE, TERMS) \
     return col_launch_one<SROW, GRAD, MODE, TERMS>(A, grid, nt, smem, st)
     if (mode == MODE_PLAIN) {

@@ -536,15 +536,28 @@ extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
         LossParams P[USL_MAX_SCALES];
         rc = fill_all(cfgs, scales, n_scales, false, P);
         if (rc != USL_OK) return rc;
+        if (gout_disp && gout_err && col_eligible(cfgs, scales, n_scales)) {
+            // column kernels store, then the scatter adds its part
+            if (stages & USL_BWD_STAGE_MAIN) {
+                if (!try_col(cfgs, scales, n_scales, true, nullptr, gout_disp,
+                             gout_err, 0, 0, (cudaStream_t)stream, &rc))
+                    rc = USL_ERR_UNSUPPORTED;
+                if (rc != USL_OK && rc != USL_ERR_UNSUPPORTED) return rc;
+            }
+            if (rc == USL_OK) {
+                launch_scatter(P, n_scales, gout_disp, gout_err, 0.0f, 0,
+                               (stages & USL_BWD_STAGE_SCATTER) != 0,
+                               (cudaStream_t)stream, &rc,
+                               (stages & USL_BWD_STAGE_MAIN) ? 1 : 0);
+                return rc;
+            }
+            rc = USL_OK;
+        }
         launch_scatter(P, n_scales, gout_disp, gout_err, 0.0f, 0,
                        (stages & USL_BWD_STAGE_SCATTER) != 0,
                        (cudaStream_t)stream, &rc);
         if (rc != USL_OK) return rc;
         if (!(stages & USL_BWD_STAGE_MAIN)) return USL_OK;
-        if (gout_disp && gout_err &&
-            try_col(cfgs, scales, n_scales, true, nullptr, gout_disp,
-                    gout_err, 1, 0, (cudaStream_t)stream, &rc))
-            return rc;
         if (gout_disp && gout_err &&
             try_march(cfgs, scales, n_scales, true, nullptr, gout_disp,
                       gout_err, 1, 0, (cudaStream_t)stream, &rc))
