@@ -185,10 +185,11 @@ def test_total_loss_matches_reference_fixture(dev, name, materialise):
 
 @pytest.mark.parametrize('loss_type', ['l1', 'bayesian', 'log_bayesian'])
 @pytest.mark.parametrize('shape', [(2, 64, 128, 0.3), (1, 96, 160, 1.0),
-                                   (3, 40, 600, 0.3)])
+                                   (3, 40, 600, 0.3), (1, 33, 77, 0.5)])
 def test_total_loss_matches_oracle(dev, loss_type, shape):
     """Seeded inputs, CPU oracle in fp64; (3,40,600) spans several column
-    tiles and exercises the seams."""
+    tiles and exercises the seams; (1,33,77): odd sizes, units that do not
+    fill their warps, unaligned rows (no bulk copies)."""
     from oracle import loss_port as P
     from oracle.make_golden import loss_config, make_inputs
     b, h, w, scale = shape

@@ -46,53 +46,61 @@ __device__ __forceinline__ unsigned desc_key(float v) {
 }
 
 // ---- pool ---------------------------------------------------------------
-// Each thread produces PX horizontally adjacent outputs so a window row is
-// loaded once and feeds PX accumulators; every accumulator still adds its
-// k*k values one by one in row-major order.
-constexpr int PX = 4;
+// grid (column groups, output rows, maps).  Each thread produces PX horizontally
+// adjacent outputs, so a window row is loaded once -- as 128-bit loads where the
+// row allows it (the loads of a warp then cover one contiguous span: this
+// kernel is bound by L1 wavefronts otherwise) -- and feeds PX accumulators;
+// every accumulator still adds its k*k values one by one in row-major order.
+constexpr int PX = 8;
 constexpr int KMAX = 15;
+constexpr int POOL_THREADS = 128;
+constexpr int PV = (KMAX + PX - 1 + 3) / 4 * 4;     // values held per window row
 
-__global__ void __launch_bounds__(256)
-pool_kernel(const float* __restrict__ in, int rows, int H, int W, int k,
+__global__ void __launch_bounds__(POOL_THREADS)
+pool_kernel(const float* __restrict__ in, int H, int W, int k, int vec_ok,
             float* __restrict__ out_val, unsigned* __restrict__ out_key) {
     const int oh = H - k + 1, ow = W - k + 1;
-    const int gx = (ow + PX - 1) / PX;
-    const long long total = (long long)rows * oh * gx;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int ox = (blockIdx.x * POOL_THREADS + threadIdx.x) * PX;
+    if (ox >= ow) return;
+    const int oy = blockIdx.y, row = blockIdx.z;
     const float div = (float)(k * k);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-         i < total; i += stride) {
-        const int xg = (int)(i % gx);
-        const int oy = (int)((i / gx) % oh);
-        const int row = (int)(i / ((long long)gx * oh));
-        const int ox = xg * PX;
-        const float* p = in + ((long long)row * H + oy) * W + ox;
-        float acc[PX];
+    const float* p = in + ((long long)row * H + oy) * W + ox;
+    const int need = k + PX - 1;
+    const bool vec = vec_ok && ox + ((need + 3) & ~3) <= W;
+    float acc[PX];
 #pragma unroll
-        for (int j = 0; j < PX; ++j) acc[j] = 0.0f;
-        for (int dy = 0; dy < k; ++dy) {
-            float v[KMAX + PX - 1];
+    for (int j = 0; j < PX; ++j) acc[j] = 0.0f;
+    for (int dy = 0; dy < k; ++dy) {
+        float v[PV];
+        if (vec) {
 #pragma unroll
-            for (int j = 0; j < KMAX + PX - 1; ++j)
-                v[j] = (j < k + PX - 1 && ox + j < W) ? __ldg(p + j) : 0.0f;
-#pragma unroll
-            for (int dx = 0; dx < KMAX; ++dx)
-                if (dx < k) {
-#pragma unroll
-                    for (int j = 0; j < PX; ++j)
-                        acc[j] = __fadd_rn(acc[j], v[dx + j]);
-                }
-            p += W;
-        }
-        const long long o = ((long long)row * oh + oy) * ow + ox;
-#pragma unroll
-        for (int j = 0; j < PX; ++j)
-            if (ox + j < ow) {
-                const float m = __fdiv_rn(acc[j], div);
-                if (out_val) out_val[o + j] = m;
-                if (out_key) out_key[o + j] = desc_key(m);
+            for (int j = 0; j < PV; j += 4) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < need) t = __ldg(reinterpret_cast<const float4*>(p + j));
+                v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < PV; ++j)
+                v[j] = (j < need && ox + j < W) ? __ldg(p + j) : 0.0f;
+        }
+#pragma unroll
+        for (int dx = 0; dx < KMAX; ++dx)
+            if (dx < k) {
+#pragma unroll
+                for (int j = 0; j < PX; ++j)
+                    acc[j] = __fadd_rn(acc[j], v[dx + j]);
+            }
+        p += W;
     }
+    const long long o = ((long long)row * oh + oy) * ow + ox;
+#pragma unroll
+    for (int j = 0; j < PX; ++j)
+        if (ox + j < ow) {
+            const float m = __fdiv_rn(acc[j], div);
+            if (out_val) out_val[o + j] = m;
+            if (out_key) out_key[o + j] = desc_key(m);
+        }
 }
 
 __global__ void __launch_bounds__(256)
@@ -124,29 +132,62 @@ hist_kernel(const unsigned* __restrict__ keys, int n, int ntiles, int shift,
     counts[((long long)row * RADIX + threadIdx.x) * ntiles + tile] = h[threadIdx.x];
 }
 
-// exclusive scan of the (digit-major, tile-minor) counts of one row
-__global__ void __launch_bounds__(1024)
-scan_kernel(unsigned* __restrict__ counts, int m) {
-    __shared__ unsigned part[1024];
-    unsigned* c = counts + (long long)blockIdx.x * m;
-    const int per = (m + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(m, lo + per);
-    unsigned s = 0;
-    for (int i = lo; i < hi; ++i) s += c[i];
-    part[threadIdx.x] = s;
+// Exclusive scan of the (digit-major, tile-minor) counts of every row, in two
+// levels so that the whole GPU works on it: scan_tiles scans the tiles of one
+// (row, digit) in place and leaves the digit's total; scan_digits turns the 256
+// totals of a row into exclusive digit bases.  scatter_kernel adds the two.
+__global__ void __launch_bounds__(256)
+scan_tiles_kernel(unsigned* __restrict__ counts, int ntiles,
+                  unsigned* __restrict__ totals) {
+    __shared__ unsigned wsum[8];
+    const int digit = blockIdx.x, row = blockIdx.y;
+    unsigned* c = counts + ((long long)row * RADIX + digit) * ntiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned carry = 0;
+    for (int base = 0; base < ntiles; base += 256) {
+        const int i = base + threadIdx.x;
+        const unsigned v = i < ntiles ? c[i] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const unsigned t = wsum[w];
+            if (w < warp) wbase += t;
+            total += t;
+        }
+        if (i < ntiles) c[i] = carry + wbase + incl - v;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[row * RADIX + digit] = carry;
+}
+
+__global__ void __launch_bounds__(RADIX)
+scan_digits_kernel(unsigned* __restrict__ totals) {
+    __shared__ unsigned wsum[RADIX / 32];
+    unsigned* t = totals + (long long)blockIdx.x * RADIX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned v = t[threadIdx.x];
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {      // Hillis-Steele, inclusive
-        unsigned v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    unsigned run = part[threadIdx.x] - s;           // exclusive base
-    for (int i = lo; i < hi; ++i) {
-        const unsigned v = c[i];
-        c[i] = run;
-        run += v;
-    }
+    unsigned wbase = 0;
+#pragma unroll
+    for (int w = 0; w < RADIX / 32; ++w)
+        if (w < warp) wbase += wsum[w];
+    t[threadIdx.x] = wbase + incl - v;
 }
 
 template <bool WITH_IDX>
@@ -155,7 +196,8 @@ scatter_kernel(const unsigned* __restrict__ keys_in,
                const float* __restrict__ vals_in, const int* __restrict__ idx_in,
                unsigned* __restrict__ keys_out, float* __restrict__ vals_out,
                int* __restrict__ idx_out, const unsigned* __restrict__ offsets,
-               int n, int ntiles, int shift) {
+               const unsigned* __restrict__ digit_base, int n, int ntiles,
+               int shift) {
     __shared__ unsigned whist[SORT_WARPS][RADIX];
     const int row = blockIdx.y, tile = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,7 +225,8 @@ scatter_kernel(const unsigned* __restrict__ keys_in,
     __syncthreads();
     {   // digit threadIdx.x: exclusive bases over the warps of this tile
         const int d = threadIdx.x;
-        unsigned base = offsets[((long long)row * RADIX + d) * ntiles + tile];
+        unsigned base = offsets[((long long)row * RADIX + d) * ntiles + tile] +
+                        digit_base[row * RADIX + d];
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w) {
             const unsigned t = whist[w][d];
@@ -289,7 +332,7 @@ static SparsLayout layout(int rows, int H, int W, int k, bool with_idx) {
         L.idx[i] = off;
         if (with_idx) off = align_up(off + e * 4);
     }
-    L.counts = off; off = align_up(off + (size_t)rows * RADIX * L.ntiles * 4);
+    L.counts = off; off = align_up(off + (size_t)rows * RADIX * (L.ntiles + 1) * 4);
     L.seg = off; off = align_up(off + (size_t)rows * USL_MAX_STEPS * 8);
     L.total = off;
     return L;
@@ -345,12 +388,17 @@ extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
     double* seg = (double*)(ws + L.seg);
     const int n = L.n, ntiles = L.ntiles;
 
-    const long long pool_threads =
-        (long long)rows * (H - k + 1) * ((W - k + 1 + PX - 1) / PX);
-    pool_kernel<<<flat_grid(pool_threads), 256, 0, stream>>>(
-        oracle, rows, H, W, k, vals[0], nullptr);
-    pool_kernel<<<flat_grid(pool_threads), 256, 0, stream>>>(
-        predicted, rows, H, W, k, pooled_pred_out, keys[0]);
+    unsigned* digit_base = counts + (size_t)rows * RADIX * ntiles;
+    {
+        const int oh = H - k + 1, ow = W - k + 1;
+        if (oh > 65535 || rows > 65535) return USL_ERR_UNSUPPORTED;
+        const dim3 pgrid(((ow + PX - 1) / PX + POOL_THREADS - 1) / POOL_THREADS, oh, rows);
+        const int vo = (W % 4 == 0) && (((uintptr_t)oracle & 15) == 0);
+        const int vp = (W % 4 == 0) && (((uintptr_t)predicted & 15) == 0);
+        pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], nullptr);
+        pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(predicted, H, W, k, vp,
+                                                        pooled_pred_out, keys[0]);
+    }
     if (pooled_oracle_out)
         if (cudaMemcpyAsync(pooled_oracle_out, vals[0], (size_t)rows * n * 4,
                             cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
@@ -364,15 +412,16 @@ extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
         const int shift = pass * 8;
         hist_kernel<<<grid, SORT_THREADS, 0, stream>>>(keys[cur], n, ntiles,
                                                        shift, counts);
-        scan_kernel<<<rows, 1024, 0, stream>>>(counts, RADIX * ntiles);
+        scan_tiles_kernel<<<dim3(RADIX, rows), 256, 0, stream>>>(counts, ntiles, digit_base);
+        scan_digits_kernel<<<rows, RADIX, 0, stream>>>(digit_base);
         if (with_idx)
             scatter_kernel<true><<<grid, SORT_THREADS, 0, stream>>>(
                 keys[cur], vals[cur], idx[cur], keys[cur ^ 1], vals[cur ^ 1],
-                idx[cur ^ 1], counts, n, ntiles, shift);
+                idx[cur ^ 1], counts, digit_base, n, ntiles, shift);
         else
             scatter_kernel<false><<<grid, SORT_THREADS, 0, stream>>>(
                 keys[cur], vals[cur], nullptr, keys[cur ^ 1], vals[cur ^ 1],
-                nullptr, counts, n, ntiles, shift);
+                nullptr, counts, digit_base, n, ntiles, shift);
         cur ^= 1;
     }
     if (with_idx)
