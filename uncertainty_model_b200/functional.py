@@ -165,7 +165,8 @@ def plan_rows(cfg_arr, sc_arr, n: int, mode: int) -> Optional[List[int]]:
 
 def loss_forward(cfgs: Sequence[UslLossConfig],
                  scales: Sequence[UslLossScale], device,
-                 reduce_group=None, with_grad: bool = False
+                 reduce_group=None, with_grad: bool = False,
+                 arrays=None, starts: Optional[List[int]] = None
                  ) -> Tuple[Tensor, Tensor, Tensor]:
     """One fused launch over all scales.
 
@@ -178,8 +179,11 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
     has checked with `plan_rows(..., MODE_GRAD)` that it applies."""
     L = lib()
     n = len(scales)
-    cfg_arr, sc_arr = _array(UslLossConfig, cfgs), _array(UslLossScale, scales)
-    starts = plan_rows(cfg_arr, sc_arr, n, MODE_GRAD if with_grad else MODE_FWD)
+    cfg_arr, sc_arr = arrays if arrays is not None else (
+        _array(UslLossConfig, cfgs), _array(UslLossScale, scales))
+    if starts is None:
+        starts = plan_rows(cfg_arr, sc_arr, n,
+                           MODE_GRAD if with_grad else MODE_FWD)
     partials = torch.empty(starts[-1] * USL_NUM_TERMS, dtype=torch.float32,
                            device=device)
     sums = torch.empty(n, USL_NUM_TERMS, dtype=torch.float64, device=device)
@@ -230,15 +234,16 @@ def loss_backward(cfgs: Sequence[UslLossConfig],
           'usl_loss_bwd')
 
 
-def loss_regrad(cfgs: Sequence[UslLossConfig], scales: Sequence[UslLossScale],
-                g_disp: Tensor, g_err: Tensor, device) -> None:
-    """Backward half of the one-pass scheme: the gradients written by the
+def loss_regrad(arrays, n_scales: int, g_disp: Tensor, g_err: Tensor,
+                device) -> None:
+    """Backward half of the one-pass scheme (`arrays`: the launch description
+    of the forward): the gradients written by the
     forward are exact for unit upstream gradients; this launch recomputes them
     for any other upstream pair and returns at once (on the device -- no host
     synchronisation) when both are 1."""
     stream = torch.cuda.current_stream(device).cuda_stream
-    check(lib().usl_loss_grad(_array(UslLossConfig, cfgs),
-                              _array(UslLossScale, scales), len(scales),
+    cfg_arr, sc_arr = arrays
+    check(lib().usl_loss_grad(cfg_arr, sc_arr, n_scales,
                               g_disp.data_ptr(), g_err.data_ptr(), None,
                               GRAD_SKIP_IF_UNIT, stream), 'usl_loss_grad')
 
@@ -483,12 +488,20 @@ class FusedLoss(torch.autograd.Function):
             cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
                                             grads, errs)
             n = len(scales)
-            if plan_rows(_array(UslLossConfig, cfgs),
-                         _array(UslLossScale, scales), n,
-                         MODE_GRAD) is not None:
-                out_disp, out_err, sums = loss_forward(cfgs, scales, device,
-                                                       group, with_grad=True)
+            arrays = (_array(UslLossConfig, cfgs), _array(UslLossScale, scales))
+            starts = plan_rows(arrays[0], arrays[1], n, MODE_GRAD)
+            if starts is not None:
+                out_disp, out_err, sums = loss_forward(
+                    cfgs, scales, device, group, with_grad=True, arrays=arrays,
+                    starts=starts)
                 ctx.onepass = grads
+                # the same launch description serves the backward: the tensors
+                # it points to are kept alive by save_for_backward / `grads`;
+                # the error maps are outputs the caller may drop, so the
+                # backward must not write them again
+                for i in range(n):
+                    arrays[1][i].err_out = None
+                ctx.arrays = arrays
                 ctx.save_for_backward(*tensors)
                 ctx.mark_non_differentiable(sums, *errs)
                 ctx.set_materialize_grads(False)
@@ -517,9 +530,8 @@ class FusedLoss(torch.autograd.Function):
             zero = None
             if g_disp is None or g_err is None:
                 zero = torch.zeros((), dtype=torch.float32, device=device)
-            cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
-                                            grads)
-            loss_regrad(cfgs, scales, zero if g_disp is None else g_disp,
+            loss_regrad(ctx.arrays, len(specs),
+                        zero if g_disp is None else g_disp,
                         zero if g_err is None else g_err, device)
             return (None, None, None) + tuple(
                 g if need else None for g, need in zip(grads, needs))
