@@ -4,15 +4,17 @@
 // align_corners=True bilinear taps; level 0 is the input itself and is
 // aliased by the host, never copied.  All levels >= 1 are produced by one
 // launch, largest level first: a CTA owns a tile of consecutive output rows of
-// one (level, sample, channel) plane, a thread one output column of one of
-// those rows, so the only integer divisions are two 32-bit ones per thread and
-// the four taps of a warp read two contiguous runs of the source rows.
+// one (level, sample, channel) plane; a thread keeps one output column (its
+// horizontal taps are computed once) and walks down the rows of the tile, so
+// an output costs ~30 instructions and the four taps of a warp read two
+// contiguous runs of the source rows.
 // HBM-bound: 24 B read + 7.875 B written per full-resolution pixel.
 #include "usl_common.cuh"
 
 namespace usl {
 
 constexpr int PYR_THREADS = 256;
+constexpr int PYR_ROWS = 8;        // output rows per thread
 
 struct PyramidParams {
     const float* src;
@@ -39,32 +41,38 @@ pyramid_kernel(const __grid_constant__ PyramidParams p) {
     const float* s = p.src + b * p.src_bs + c * p.src_cs;
     float* d = p.dst[l] + (long long)plane_i * h * w;
     const int y0 = tile * p.rows[l];
+    const int y1 = min(h, y0 + p.rows[l]);
+    const float sy = p.sy[l];
     if (w <= PYR_THREADS) {
+        const int rstep = PYR_THREADS / w;          // rows the block covers at once
         const int ry = threadIdx.x / w, x = threadIdx.x - ry * w;
-        const int y = y0 + ry;
-        if (ry >= p.rows[l] || y >= h) return;
-        const TapAC ty = ac_taps(y, p.sy[l], p.H);
+        if (ry >= rstep) return;
         const TapAC tx = ac_taps(x, p.sx[l], p.W);
-        const float* r0 = s + (long long)ty.i0 * p.W;
-        const float* r1 = s + (long long)ty.i1 * p.W;
-        const float v00 = __ldg(r0 + tx.i0), v01 = __ldg(r0 + tx.i1);
-        const float v10 = __ldg(r1 + tx.i0), v11 = __ldg(r1 + tx.i1);
-        // ATen: w0y * (w0x * v00 + w1x * v01) + w1y * (w0x * v10 + w1x * v11)
-        const float top = tx.w0 * v00 + tx.w1 * v01;
-        const float bot = tx.w0 * v10 + tx.w1 * v11;
-        d[(long long)y * w + x] = ty.w0 * top + ty.w1 * bot;
-    } else {
-        if (y0 >= h) return;
-        const TapAC ty = ac_taps(y0, p.sy[l], p.H);
-        const float* r0 = s + (long long)ty.i0 * p.W;
-        const float* r1 = s + (long long)ty.i1 * p.W;
-        for (int x = threadIdx.x; x < w; x += PYR_THREADS) {
-            const TapAC tx = ac_taps(x, p.sx[l], p.W);
-            const float v00 = __ldg(r0 + tx.i0), v01 = __ldg(r0 + tx.i1);
-            const float v10 = __ldg(r1 + tx.i0), v11 = __ldg(r1 + tx.i1);
+        const float* s0 = s + tx.i0;
+        const float* s1 = s + tx.i1;
+        for (int y = y0 + ry; y < y1; y += rstep) {
+            const TapAC ty = ac_taps(y, sy, p.H);
+            const long long o0 = (long long)ty.i0 * p.W, o1 = (long long)ty.i1 * p.W;
+            const float v00 = __ldg(s0 + o0), v01 = __ldg(s1 + o0);
+            const float v10 = __ldg(s0 + o1), v11 = __ldg(s1 + o1);
+            // ATen: w0y * (w0x * v00 + w1x * v01) + w1y * (w0x * v10 + w1x * v11)
             const float top = tx.w0 * v00 + tx.w1 * v01;
             const float bot = tx.w0 * v10 + tx.w1 * v11;
-            d[(long long)y0 * w + x] = ty.w0 * top + ty.w1 * bot;
+            d[(long long)y * w + x] = ty.w0 * top + ty.w1 * bot;
+        }
+    } else {
+        for (int y = y0; y < y1; ++y) {
+            const TapAC ty = ac_taps(y, sy, p.H);
+            const float* r0 = s + (long long)ty.i0 * p.W;
+            const float* r1 = s + (long long)ty.i1 * p.W;
+            for (int x = threadIdx.x; x < w; x += PYR_THREADS) {
+                const TapAC tx = ac_taps(x, p.sx[l], p.W);
+                const float v00 = __ldg(r0 + tx.i0), v01 = __ldg(r0 + tx.i1);
+                const float v10 = __ldg(r1 + tx.i0), v11 = __ldg(r1 + tx.i1);
+                const float top = tx.w0 * v00 + tx.w1 * v01;
+                const float bot = tx.w0 * v10 + tx.w1 * v11;
+                d[(long long)y * w + x] = ty.w0 * top + ty.w1 * bot;
+            }
         }
     }
 }
@@ -91,7 +99,7 @@ extern "C" int usl_pyramid(const float* src, int B, int C, int H, int W,
         p.h[l] = h; p.w[l] = w;
         p.sy[l] = ac_scale(H, h);
         p.sx[l] = ac_scale(W, w);
-        p.rows[l] = w <= PYR_THREADS ? PYR_THREADS / w : 1;
+        p.rows[l] = (w <= PYR_THREADS ? PYR_THREADS / w : 1) * PYR_ROWS;
         p.tiles[l] = (h + p.rows[l] - 1) / p.rows[l];
         const long long ctas = (long long)B * C * p.tiles[l];
         if (p.cta_start[l] + ctas > 0x7fffffffLL) return USL_ERR_UNSUPPORTED;
