@@ -42,8 +42,10 @@ __device__ __forceinline__ void scatter_chunk(float* Hrow, float2* stage, int d,
     __syncwarp();
     const bool leader = d >= -1 && (grp & ((1u << lane) - 1u)) == 0u;
     if (leader) {
-        float s0 = 0.0f, s1 = 0.0f;
-        for (unsigned m = grp; m; m &= m - 1u) {
+        // own contribution first (the leader is the lowest lane), then the
+        // rest of the group in lane order; most groups are singletons
+        float s0 = a0, s1 = a1;
+        for (unsigned m = grp & (grp - 1u); m; m &= m - 1u) {
             const float2 c = stage[__ffs(m) - 1];
             s0 += c.x; s1 += c.y;
         }
@@ -56,6 +58,9 @@ __device__ __forceinline__ void scatter_chunk(float* Hrow, float2* stage, int d,
     //  barrier after the next chunk's staging orders these updates before its)
 }
 
+// ALIGNED: every row width of the launch is a multiple of 32 (a chunk is either
+// wholly inside its row or wholly outside).
+template <bool ALIGNED>
 __global__ void __launch_bounds__(CONS2_THREADS, 2)
 cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
     extern __shared__ float4 smem_raw[];
@@ -119,12 +124,12 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     const int x = span + j * 32 + lane;
-                    c0[j] = x < w ? __ldg(pa + x) : 0.0f;
+                    c0[j] = (ALIGNED ? span + j * 32 < w : x < w) ? __ldg(pa + x) : 0.0f;
                 }
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     const int x = span + j * 32 + lane;
-                    const bool valid = x < w;
+                    const bool valid = ALIGNED ? span + j * 32 < w : x < w;
                     const float a = c0[j];
                     // warp_coord(x, w, sign * a) with the base grid from the table
                     const float g = fmaf(2.0f, xb[valid ? x : 0] + sign * a, -1.0f);
@@ -201,11 +206,21 @@ int cons_scatter2_launch(MultiCons* C, cudaStream_t st) {
         if (bytes > smem) smem = bytes;
     }
     if (smem > 220 * 1024) return USL_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(cons_scatter2_kernel,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem) != cudaSuccess)
-        return USL_ERR_CUDA;
-    cons_scatter2_kernel<<<C->cta_start[C->n], CONS2_THREADS, smem, st>>>(*C);
+    bool aligned = true;
+    for (int k = 0; k < C->n; ++k) aligned = aligned && (C->P[k].w % 32 == 0);
+    if (aligned) {
+        if (cudaFuncSetAttribute(cons_scatter2_kernel<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return USL_ERR_CUDA;
+        cons_scatter2_kernel<true><<<C->cta_start[C->n], CONS2_THREADS, smem, st>>>(*C);
+    } else {
+        if (cudaFuncSetAttribute(cons_scatter2_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return USL_ERR_CUDA;
+        cons_scatter2_kernel<false><<<C->cta_start[C->n], CONS2_THREADS, smem, st>>>(*C);
+    }
     return check_launch();
 }
 
