@@ -24,20 +24,22 @@
 
 namespace usl {
 
-constexpr int CONS2_THREADS = 384;   // 12 warps: 2 * (16 + 2) jobs = 3 each
+constexpr int CONS2_THREADS = 512;   // 16 warps: 2 * (14 + 2) jobs = 2 each
+constexpr int CONS2_R = 14;          // destination rows per CTA
 constexpr int HPAD = 2;              // absorbs taps that fall outside the row
-constexpr int NCH = 16;              // chunks of 32 pixels per span (registers)
+constexpr int NCH = 8;               // chunks of 32 pixels per span (registers)
 
 // One chunk of 32 sources into H.  `d`: destination column of the first tap
 // (dead lanes: a unique key below -1; they write nothing).  Lanes that share a
-// destination form a group (match.any); the contributions of the chunk are
+// destination form a group (`grp`, from match.any -- issued by the caller for a
+// whole span at once: the unit is slow and its latency long); the contributions of the chunk are
 // staged in shared memory and each group LEADER -- its lowest lane -- adds up
 // those of its group in lane order (a private, collective-free loop), then the
 // leaders, whose destinations are distinct, update H: first taps, then second.
 // `stage`: 32 entries; consecutive calls must alternate between two buffers.
 __device__ __forceinline__ void scatter_chunk(float* Hrow, float2* stage, int d,
-                                              float a0, float a1, int lane) {
-    const unsigned grp = __match_any_sync(0xffffffffu, d);
+                                              unsigned grp, float a0, float a1,
+                                              int lane) {
     stage[lane] = make_float2(a0, a1);
     __syncwarp();
     const bool leader = d >= -1 && (grp & ((1u << lane) - 1u)) == 0u;
@@ -71,8 +73,9 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
     const float ge_up = P.gout_e ? __ldg(P.gout_e) : P.gout_default;
     if (M.skip_if_unit && gd_up == 1.0f && ge_up == 1.0f) return;
     const int local = blockIdx.x - M.cta_start[s];
-    const int b = local / M.strips[s];
-    const int ya = (local % M.strips[s]) * P.R;
+    // strip-major: the (short) last strips of all samples come last
+    const int b = local % P.B;
+    const int ya = (local / P.B) * P.R;
     const int yb = min(P.h, ya + P.R);
     const int w = P.w, h = P.h;
     const int HW = w + 2 * HPAD;
@@ -121,6 +124,7 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
             for (int span = 0; span < w; span += 32 * NCH) {
                 float c0[NCH], c1[NCH];
                 int dst[NCH];
+                unsigned grp[NCH];
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     const int x = span + j * 32 + lane;
@@ -144,11 +148,12 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
                     dst[j] = live ? xi : -1000 - lane;
                     c0[j] = -rr * tx.w0;
                     c1[j] = -rr * tx.w1;
+                    grp[j] = __match_any_sync(0xffffffffu, dst[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     if (span + j * 32 >= w) break;
-                    scatter_chunk(Hrow, stage + (j & 1) * 32, dst[j], c0[j], c1[j], lane);
+                    scatter_chunk(Hrow, stage + (j & 1) * 32, dst[j], grp[j], c0[j], c1[j], lane);
                 }
             }
         }
@@ -191,12 +196,12 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
 }
 
 int cons_scatter2_launch(MultiCons* C, cudaStream_t st) {
-    // strips of 16 destination rows: 2 * 18 jobs over 12 warps
+    // strips of 14 destination rows: 2 * 16 jobs over 16 warps, two CTAs per SM
     size_t smem = 0;
     C->cta_start[0] = 0;
     for (int k = 0; k < C->n; ++k) {
         ConsParams& c = C->P[k];
-        c.R = 16;
+        c.R = CONS2_R;
         if (c.R > c.h) c.R = c.h;
         C->strips[k] = (c.h + c.R - 1) / c.R;
         C->cta_start[k + 1] = C->cta_start[k] + C->strips[k] * c.B;
