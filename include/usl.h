@@ -163,6 +163,13 @@ int usl_loss_bwd(const UslLossConfig* cfgs, const UslLossScale* scales,
  * CTA then returns at once if they are both 1 (nothing to redo), and
  * recomputes the gradients otherwise.  No host synchronisation either way. */
 #define USL_GRAD_SKIP_IF_UNIT 1
+/* The launch sequence in two halves, so that a caller can put work that only
+ * needs the partial sums (their reduction, an all-reduce across ranks) between
+ * them: NO_SCATTER = the fused kernels only (sums and gradients but for the
+ * transposed warp of the consistency terms), ONLY_SCATTER = that missing part,
+ * added to grad_disp.  Neither flag = both, in this order. */
+#define USL_GRAD_NO_SCATTER 2
+#define USL_GRAD_ONLY_SCATTER 4
 int usl_loss_grad(const UslLossConfig* cfgs, const UslLossScale* scales,
                   int n_scales, const float* gout_disp, const float* gout_err,
                   float* partials, int flags, void* stream);

@@ -362,6 +362,16 @@ static int try_col(const UslLossConfig* cfgs, const UslLossScale* scales,
     return 1;
 }
 
+// Whether try_col will take this call (eligible AND plannable).
+static bool col_ready(const UslLossConfig* cfgs, const UslLossScale* scales, int n,
+                      bool grad) {
+    if (!col_eligible(cfgs, scales, n)) return false;
+    ColPlan M;
+    M.n = n;
+    if (fill_all(cfgs, scales, n, false, M.P) != USL_OK) return false;
+    return col_plan(&M, grad) == USL_OK;
+}
+
 // The marching path, if every scale qualifies: 1 = launched, 0 = not eligible.
 static int try_march(const UslLossConfig* cfgs, const UslLossScale* scales,
                      int n, bool grad, float* partials, const float* gout_d,
@@ -507,13 +517,20 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
     const int skip = (flags & USL_GRAD_SKIP_IF_UNIT) ? 1 : 0;
     // column kernels: they store the gradient, then the scatter adds its part
     // (the read-modify-write sits in the kernel that has warps to spare)
-    if (try_col(cfgs, scales, n_scales, true, partials, gout_disp, gout_err, 0,
-                skip, (cudaStream_t)stream, &rc)) {
-        if (rc != USL_OK) return rc;
-        launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
-                       (cudaStream_t)stream, &rc, 1);
+    if (col_ready(cfgs, scales, n_scales, true)) {
+        if (!(flags & USL_GRAD_ONLY_SCATTER)) {
+            if (!try_col(cfgs, scales, n_scales, true, partials, gout_disp,
+                         gout_err, 0, skip, (cudaStream_t)stream, &rc))
+                return USL_ERR_UNSUPPORTED;
+            if (rc != USL_OK) return rc;
+        }
+        if (!(flags & USL_GRAD_NO_SCATTER))
+            launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
+                           (cudaStream_t)stream, &rc, 1);
         return rc;
     }
+    // (other kernels: the scatter comes first; everything in the first half)
+    if (flags & USL_GRAD_ONLY_SCATTER) return USL_OK;
     launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
                    (cudaStream_t)stream, &rc);
     if (rc != USL_OK) return rc;

@@ -149,7 +149,7 @@ def _array(cls, items):
 # launches
 # --------------------------------------------------------------------------
 MODE_FWD, MODE_GRAD = 0, 1
-GRAD_SKIP_IF_UNIT = 1
+GRAD_SKIP_IF_UNIT, GRAD_NO_SCATTER, GRAD_ONLY_SCATTER = 1, 2, 4
 
 
 def plan_rows(cfg_arr, sc_arr, n: int, mode: int) -> Optional[List[int]]:
@@ -191,15 +191,26 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
     out_err = torch.empty((), dtype=torch.float32, device=device)
     coef = coef_tensor(tuple(tuple(c.coef) for c in cfgs), device)
     stream = _stream(partials)
+    # sharded batch + gradients: the all-reduce of the sums only needs the fused
+    # kernels, so it runs (NCCL stream) while the scatter kernel works
+    split = with_grad and reduce_group is not None
     if with_grad:
         check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None,
-                              partials.data_ptr(), 0, stream), 'usl_loss_grad')
+                              partials.data_ptr(),
+                              GRAD_NO_SCATTER if split else 0, stream),
+              'usl_loss_grad')
     else:
         check(L.usl_loss_fwd(cfg_arr, sc_arr, n, partials.data_ptr(), stream),
               'usl_loss_fwd')
     check(L.usl_loss_reduce(partials.data_ptr(), (C.c_int * (n + 1))(*starts),
                             n, sums.data_ptr(), stream), 'usl_loss_reduce')
-    if reduce_group is not None:
+    if split:
+        work = torch.distributed.all_reduce(sums, group=reduce_group,
+                                            async_op=True)
+        check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None, None,
+                              GRAD_ONLY_SCATTER, stream), 'usl_loss_grad')
+        work.wait()
+    elif reduce_group is not None:
         torch.distributed.all_reduce(sums, group=reduce_group)
     check(L.usl_loss_combine(sums.data_ptr(), coef.data_ptr(), n,
                              out_disp.data_ptr(), out_err.data_ptr(), stream),
