@@ -110,11 +110,11 @@ typedef struct UslLossScale {
 /* All pyramid scales of a step are processed by ONE launch: `cfgs` and
  * `scales` are HOST arrays of n_scales entries (largest scale first).
  *
- * Two kernel families sit behind these entry points.  The register-marching
- * kernels (csrc/march_core.cuh) take every call whose scales all warp
- * in-kernel (no recon_in / err_in), have the reprojection term on and an even
- * width -- the training step; everything else (given reconstructions or error
- * maps, stand-alone terms, odd widths) runs on the general strip kernels
+ * Two kernel families sit behind these entry points.  The column-marching
+ * kernels (csrc/col_core.cuh) take every call whose scales all warp in-kernel
+ * (no recon_in / err_in) and have the reprojection term on -- the training
+ * step; everything else (given reconstructions or error maps, stand-alone
+ * terms, rows too small) runs on the general strip kernels
  * (csrc/loss_core.cuh).
  *
  * usl_loss_plan: row offsets into `partials` (USL_NUM_TERMS floats per row) of

@@ -14,8 +14,6 @@ from uncertainty_model_b200.functional import (LossSettings, make_config,
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'emu', 'emu.cpp')
 OUT = os.path.join(HERE, 'emu', 'build', 'libemu.so')
-SRC_MARCH = os.path.join(HERE, 'emu', 'emu_march.cpp')
-OUT_MARCH = os.path.join(HERE, 'emu', 'build', 'libemu_march.so')
 SRC_COL = os.path.join(HERE, 'emu', 'emu_col.cpp')
 OUT_COL = os.path.join(HERE, 'emu', 'build', 'libemu_col.so')
 CSRC = os.path.join(os.path.dirname(HERE), 'uncertainty_model_b200', 'csrc')
@@ -85,70 +83,6 @@ def emu_scale(settings: LossSettings, terms, coefs, images, pred, *, recon=None,
                        (C.c_float * 2)(*g))
         out.update(grad_pred=grad_pred, grad_recon=grad_recon)
     return out
-
-
-_emu_march = None
-
-
-def emu_march():
-    global _emu_march
-    if _emu_march is None:
-        deps = [SRC_MARCH] + [os.path.join(CSRC, f) for f in
-                              ('march_core.cuh', 'loss_core.cuh',
-                               'usl_math.cuh')]
-        if not os.path.exists(OUT_MARCH) or any(
-                os.path.getmtime(d) > os.path.getmtime(OUT_MARCH)
-                for d in deps):
-            os.makedirs(os.path.dirname(OUT_MARCH), exist_ok=True)
-            subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC',
-                            '-ffp-contract=off', '-x', 'c++', SRC_MARCH, '-o',
-                            OUT_MARCH], check=True)
-        lib = C.CDLL(OUT_MARCH)
-        lib.emu_march_fwd.restype = C.c_int
-        lib.emu_march_fwd.argtypes = [C.POINTER(UslLossConfig),
-                                      C.POINTER(UslLossScale), C.c_int,
-                                      C.c_int, C.POINTER(C.c_double)]
-        lib.emu_march_grad.restype = C.c_int
-        lib.emu_march_grad.argtypes = [C.POINTER(UslLossConfig),
-                                       C.POINTER(UslLossScale), C.c_int,
-                                       C.c_int, C.c_int, C.POINTER(C.c_float),
-                                       C.POINTER(C.c_double)]
-        _emu_march = lib
-    return _emu_march
-
-
-def emu_march_scale(settings: LossSettings, terms, coefs, images, pred, *,
-                    g=(1.0, 1.0), TW=256, R=16, consR=16, want_recon=False,
-                    grad_recon_in=None):
-    """The marching kernels (forward-only mode, then the one-pass
-    sums+gradient mode on top of the emulated scatter) for ONE scale.
-
-    Returns dict(sums, sums_grad, err, recon, grad_pred)."""
-    L = emu_march()
-    b, _, h, w = pred.shape
-    images = images.contiguous()
-    pred = pred.contiguous()
-    cfg = make_config(terms, settings, coefs)
-    err_out = torch.full((b, 2, h, w), float('nan'))
-    recon_out = torch.full((b, 6, h, w), float('nan')) if want_recon else None
-    sc = make_scale(images, pred[:, 0:2], pred[:, 2:4], shape=(b, h, w),
-                    err_out=err_out, recon_out=recon_out)
-    sums = (C.c_double * 6)()
-    assert L.emu_march_fwd(C.byref(cfg), C.byref(sc), TW, R, sums) == 0
-    grad_pred = torch.full((b, 4, h, w), float('nan'))
-    sc = make_scale(images, pred[:, 0:2], pred[:, 2:4], shape=(b, h, w),
-                    grad_recon_in=grad_recon_in, grad_disp=grad_pred[:, 0:2],
-                    grad_unc=grad_pred[:, 2:4])
-    gout = (C.c_float * 2)(*g)
-    acc = 0
-    if terms & 34:          # TERM_CONS_D | TERM_CONS_U
-        emu().emu_cons_scatter(C.byref(cfg), C.byref(sc), consR, gout)
-        acc = 1
-    sums_g = (C.c_double * 6)()
-    assert L.emu_march_grad(C.byref(cfg), C.byref(sc), TW, R, acc, gout,
-                            sums_g) == 0
-    return dict(sums=list(sums), sums_grad=list(sums_g), err=err_out,
-                recon=recon_out, grad_pred=grad_pred)
 
 
 _emu_col = None

@@ -205,6 +205,25 @@ def test_total_loss_matches_oracle(dev, loss_type, shape):
         assert r < GRAD_REL, (i, r)
 
 
+def test_general_strip_kernels_match_oracle(dev, monkeypatch):
+    """The same training step with the column kernels switched off
+    (USL_NO_COL): forward sums, two-launch backward on the general strip
+    kernels -- the path every call the hot kernels do not take runs on."""
+    from oracle import loss_port as P
+    from oracle.make_golden import loss_config, make_inputs
+    monkeypatch.setenv('USL_NO_COL', '1')
+    cfg = loss_config('bayesian', smoothness_weight=0.25)
+    left, right, preds = make_inputs(2, 64, 128, 0.3, 33)
+    stereo = torch.cat([left, right], 1)
+    rdl, rel, rgrads = P.step(stereo.double(), [p.double() for p in preds], cfg)
+    dl, el, gp, *_ = run_ours(dev, stereo, preds, cfg)
+    assert abs(dl.item() - float(rdl)) <= LOSS_REL * abs(float(rdl))
+    assert abs(el.item() - float(rel)) <= LOSS_REL * abs(float(rel))
+    for i in range(4):
+        r = grad_err(gp[i].grad, rgrads[i].numpy(), preds[i])
+        assert r < GRAD_REL, (i, r)
+
+
 def test_separate_upstream_gradients(dev):
     """disp_loss and error_loss back-propagated with different weights."""
     from oracle import loss_port as P

@@ -14,10 +14,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libusl.so')
 SOURCES = ['pyramid.cu', 'warp.cu', 'misc.cu', 'loss_kernels.cu',
-           'march_kernels.cu', 'col_kernels.cu', 'col_inst_512.cu', 'col_inst_256.cu',
+           'col_kernels.cu', 'col_inst_512.cu', 'col_inst_256.cu',
            'col_inst_128.cu', 'col_inst_64.cu', 'cons_kernels.cu', 'spars.cu']
 HEADERS = ['usl_math.cuh', 'usl_common.cuh', 'loss_core.cuh', 'cons_core.cuh',
-           'march_core.cuh', 'march_launch.cuh', 'col_core.cuh',
+           'col_core.cuh',
            'col_launch.cuh', 'col_kernel_impl.cuh', 'cons_launch.cuh',
            os.path.join('..', '..', 'include', 'usl.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',

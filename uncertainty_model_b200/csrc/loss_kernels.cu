@@ -11,7 +11,6 @@
 #include "col_launch.cuh"
 #include "cons_core.cuh"
 #include "cons_launch.cuh"
-#include "march_launch.cuh"
 #include "usl_common.cuh"
 
 namespace usl {
@@ -305,21 +304,6 @@ extern "C" int usl_loss_plan(const UslLossConfig* cfgs,
         }
         if (rc != USL_ERR_UNSUPPORTED) return rc;
     }
-    if (march_eligible(cfgs, scales, n_scales)) {
-        MarchPlan M;
-        M.n = n_scales;
-        int rc = fill_all(cfgs, scales, n_scales, false, M.P);
-        if (rc != USL_OK) return rc;
-        rc = march_plan(&M, mode == USL_MODE_GRAD);
-        if (rc == USL_OK) {
-            // one row of partial sums per unit
-            cta_starts[0] = 0;
-            for (int i = 0; i < n_scales; ++i)
-                cta_starts[i + 1] = cta_starts[i] + M.units[i];
-            return USL_OK;
-        }
-        if (rc != USL_ERR_UNSUPPORTED) return rc;
-    }
     if (mode == USL_MODE_GRAD) return USL_ERR_UNSUPPORTED;
     MultiParams M;
     size_t smem; int nt;
@@ -372,33 +356,6 @@ static bool col_ready(const UslLossConfig* cfgs, const UslLossScale* scales, int
     return col_plan(&M, grad) == USL_OK;
 }
 
-// The marching path, if every scale qualifies: 1 = launched, 0 = not eligible.
-static int try_march(const UslLossConfig* cfgs, const UslLossScale* scales,
-                     int n, bool grad, float* partials, const float* gout_d,
-                     const float* gout_e, int accumulate, int skip_if_unit,
-                     cudaStream_t st, int* rc_out) {
-    if (!march_eligible(cfgs, scales, n)) return 0;
-    MarchPlan M;
-    M.n = n;
-    int rc = fill_all(cfgs, scales, n, false, M.P);
-    if (rc != USL_OK) { *rc_out = rc; return 1; }
-    rc = march_plan(&M, grad);
-    if (rc == USL_ERR_UNSUPPORTED) return 0;
-    if (rc != USL_OK) { *rc_out = rc; return 1; }
-    long long row = 0;
-    for (int i = 0; i < n; ++i) {
-        LossParams& p = M.P[i];
-        p.partials = partials ? partials + row * NUM_ACC : nullptr;
-        row += M.units[i];
-        p.gout_d = gout_d; p.gout_e = gout_e;
-        p.grad_disp_accumulate =
-            (accumulate && (p.terms & (TERM_CONS_D | TERM_CONS_U))) ? 1 : 0;
-        if (grad && (!p.grad_disp || !p.grad_unc)) { *rc_out = USL_ERR_ARG; return 1; }
-    }
-    *rc_out = march_launch(&M, grad, skip_if_unit, st);
-    return 1;
-}
-
 extern "C" int usl_loss_fwd(const UslLossConfig* cfgs,
                             const UslLossScale* scales, int n_scales,
                             float* partials, void* stream) {
@@ -406,9 +363,6 @@ extern "C" int usl_loss_fwd(const UslLossConfig* cfgs,
     int rc = USL_OK;
     if (try_col(cfgs, scales, n_scales, false, partials, nullptr, nullptr, 0,
                 0, (cudaStream_t)stream, &rc))
-        return rc;
-    if (try_march(cfgs, scales, n_scales, false, partials, nullptr, nullptr, 0,
-                  0, (cudaStream_t)stream, &rc))
         return rc;
     MultiParams M;
     size_t smem; int nt;
@@ -508,35 +462,22 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
                              const UslLossScale* scales, int n_scales,
                              const float* gout_disp, const float* gout_err,
                              float* partials, int flags, void* stream) {
-    if (!col_eligible(cfgs, scales, n_scales) &&
-        !march_eligible(cfgs, scales, n_scales))
-        return USL_ERR_UNSUPPORTED;
+    if (!col_ready(cfgs, scales, n_scales, true)) return USL_ERR_UNSUPPORTED;
     LossParams P[USL_MAX_SCALES];
     int rc = fill_all(cfgs, scales, n_scales, false, P);
     if (rc != USL_OK) return rc;
     const int skip = (flags & USL_GRAD_SKIP_IF_UNIT) ? 1 : 0;
     // column kernels: they store the gradient, then the scatter adds its part
     // (the read-modify-write sits in the kernel that has warps to spare)
-    if (col_ready(cfgs, scales, n_scales, true)) {
-        if (!(flags & USL_GRAD_ONLY_SCATTER)) {
-            if (!try_col(cfgs, scales, n_scales, true, partials, gout_disp,
-                         gout_err, 0, skip, (cudaStream_t)stream, &rc))
-                return USL_ERR_UNSUPPORTED;
-            if (rc != USL_OK) return rc;
-        }
-        if (!(flags & USL_GRAD_NO_SCATTER))
-            launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
-                           (cudaStream_t)stream, &rc, 1);
-        return rc;
+    if (!(flags & USL_GRAD_ONLY_SCATTER)) {
+        if (!try_col(cfgs, scales, n_scales, true, partials, gout_disp,
+                     gout_err, 0, skip, (cudaStream_t)stream, &rc))
+            return USL_ERR_UNSUPPORTED;
+        if (rc != USL_OK) return rc;
     }
-    // (other kernels: the scatter comes first; everything in the first half)
-    if (flags & USL_GRAD_ONLY_SCATTER) return USL_OK;
-    launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
-                   (cudaStream_t)stream, &rc);
-    if (rc != USL_OK) return rc;
-    if (!try_march(cfgs, scales, n_scales, true, partials, gout_disp, gout_err,
-                   1, skip, (cudaStream_t)stream, &rc))
-        return USL_ERR_UNSUPPORTED;
+    if (!(flags & USL_GRAD_NO_SCATTER))
+        launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
+                       (cudaStream_t)stream, &rc, 1);
     return rc;
 }
 
@@ -547,42 +488,25 @@ extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
     if (!(stages & (USL_BWD_STAGE_SCATTER | USL_BWD_STAGE_MAIN)))
         return USL_ERR_ARG;
     int rc = USL_OK;
-    if (col_eligible(cfgs, scales, n_scales) ||
-        march_eligible(cfgs, scales, n_scales)) {
-        // a NULL upstream gradient means "this output takes no part": 0
+    if (gout_disp && gout_err && col_ready(cfgs, scales, n_scales, true)) {
         LossParams P[USL_MAX_SCALES];
         rc = fill_all(cfgs, scales, n_scales, false, P);
         if (rc != USL_OK) return rc;
-        if (gout_disp && gout_err && col_eligible(cfgs, scales, n_scales)) {
-            // column kernels store, then the scatter adds its part
-            if (stages & USL_BWD_STAGE_MAIN) {
-                if (!try_col(cfgs, scales, n_scales, true, nullptr, gout_disp,
-                             gout_err, 0, 0, (cudaStream_t)stream, &rc))
-                    rc = USL_ERR_UNSUPPORTED;
-                if (rc != USL_OK && rc != USL_ERR_UNSUPPORTED) return rc;
-            }
-            if (rc == USL_OK) {
-                launch_scatter(P, n_scales, gout_disp, gout_err, 0.0f, 0,
-                               (stages & USL_BWD_STAGE_SCATTER) != 0,
-                               (cudaStream_t)stream, &rc,
-                               (stages & USL_BWD_STAGE_MAIN) ? 1 : 0);
-                return rc;
-            }
-            rc = USL_OK;
+        // column kernels store, then the scatter adds its part
+        if (stages & USL_BWD_STAGE_MAIN) {
+            if (!try_col(cfgs, scales, n_scales, true, nullptr, gout_disp,
+                         gout_err, 0, 0, (cudaStream_t)stream, &rc))
+                return USL_ERR_UNSUPPORTED;
+            if (rc != USL_OK) return rc;
         }
         launch_scatter(P, n_scales, gout_disp, gout_err, 0.0f, 0,
                        (stages & USL_BWD_STAGE_SCATTER) != 0,
-                       (cudaStream_t)stream, &rc);
-        if (rc != USL_OK) return rc;
-        if (!(stages & USL_BWD_STAGE_MAIN)) return USL_OK;
-        if (gout_disp && gout_err &&
-            try_march(cfgs, scales, n_scales, true, nullptr, gout_disp,
-                      gout_err, 1, 0, (cudaStream_t)stream, &rc))
-            return rc;
-        // (an absent upstream gradient is rare: fall through to the general
-        //  kernel, which treats NULL as zero)
-        stages &= ~USL_BWD_STAGE_SCATTER;
+                       (cudaStream_t)stream, &rc,
+                       (stages & USL_BWD_STAGE_MAIN) ? 1 : 0);
+        return rc;
     }
+    // (a NULL upstream gradient means "this output takes no part": the general
+    //  kernels below treat it as zero)
     MultiParams M;
     size_t smem; int nt;
     rc = plan(cfgs, scales, n_scales, true, &M, &smem, &nt);
