@@ -45,13 +45,27 @@ def planes(t: Tensor) -> Tensor:
     return t.contiguous()
 
 
-def _ptr(t: Optional[Tensor]) -> Optional[int]:
-    return None if t is None else t.data_ptr()
+class ChannelPair:
+    """Two consecutive channels of a (B,C,h,w) tensor, as the C ABI sees them
+    (base pointer, batch / channel strides) -- without building a view."""
+    __slots__ = ('ptr', 'bs', 'cs')
+
+    def __init__(self, t: Tensor, ch: int) -> None:
+        self.bs, self.cs = t.stride(0), t.stride(1)
+        self.ptr = t.data_ptr() + 4 * ch * self.cs
 
 
-def _strides(t: Optional[Tensor]) -> Tuple[int, int]:
+def _ptr(t) -> Optional[int]:
+    if t is None:
+        return None
+    return t.ptr if isinstance(t, ChannelPair) else t.data_ptr()
+
+
+def _strides(t) -> Tuple[int, int]:
     if t is None:
         return 0, 0
+    if isinstance(t, ChannelPair):
+        return t.bs, t.cs
     return t.stride(0), t.stride(1)
 
 
@@ -423,8 +437,8 @@ class ScaleSpec:
     want_err: bool = False  # also return the (B,2,h,w) error map
 
 
-def _pair(t: Tensor, ch: int) -> Tensor:
-    return t[:, ch:ch + 2]
+def _pair(t: Tensor, ch: int) -> ChannelPair:
+    return ChannelPair(t, ch)
 
 
 class FusedLoss(torch.autograd.Function):
