@@ -8,11 +8,14 @@
 // warp from start to end, into a row H of shared memory no other warp touches:
 //   * the warp blends the opposite view's disparity row it samples (Vd);
 //   * it walks the row in 32-pixel chunks, in order; the lanes of a chunk that
-//     hit the same destination column are grouped with match.any and summed by
-//     the group leader in lane order; the leaders -- whose destinations are now
-//     distinct -- add into H with plain shared-memory read-modify-writes
-//     (first tap, __syncwarp, second tap).  The order of every sum is a pure
-//     function of the data: no atomics, bit-identical run to run.
+//     hit the same destination column are grouped (contiguous runs where the
+//     destinations are monotone -- one shuffle, two votes -- else match.any)
+//     and summed by the group leader in lane order over shuffles; the leaders
+//     -- whose destinations are now distinct -- add into H with plain
+//     shared-memory read-modify-writes (first tap, __syncwarp, second tap),
+//     the other lanes into spare cells, so that nothing branches.  The order
+//     of every sum is a pure function of the data: no atomics, bit-identical
+//     run to run.
 // After ONE block barrier the destination rows are assembled from the three
 // source rows around each of them, with the vertical tap weights, and stored
 // (or added to what the fused kernel wrote before: `accumulate`).
@@ -29,35 +32,61 @@ constexpr int CONS2_R = 14;          // destination rows per CTA
 constexpr int HPAD = 2;              // absorbs taps that fall outside the row
 constexpr int NCH = 8;               // chunks of 32 pixels per span (registers)
 
+__host__ __device__ inline int xb_floats(int w) {
+    return (w + 32 * NCH - 1) / (32 * NCH) * (32 * NCH);
+}
+
 // One chunk of 32 sources into H.  `d`: destination column of the first tap
-// (dead lanes: a unique key below -1; they write nothing).  Lanes that share a
+// (dead lanes: a unique key below -1 or from DEAD_HI up; they write nothing).  Lanes that share a
 // destination form a group (`grp`, from match.any -- issued by the caller for a
-// whole span at once: the unit is slow and its latency long); the contributions of the chunk are
-// staged in shared memory and each group LEADER -- its lowest lane -- adds up
-// those of its group in lane order (a private, collective-free loop), then the
-// leaders, whose destinations are distinct, update H: first taps, then second.
-// `stage`: 32 entries; consecutive calls must alternate between two buffers.
-__device__ __forceinline__ void scatter_chunk(float* Hrow, float2* stage, int d,
+// whole span at once: the unit is slow and its latency long).  Each group
+// LEADER -- its lowest lane -- adds up the contributions of its group in lane
+// order, fetched with shuffles in a loop every lane walks together (its trip
+// count is the size of the largest group, minus one: no divergent branches);
+// then the leaders, whose destinations are distinct, update H: first taps,
+// __syncwarp, second taps.  The other lanes do the same read-modify-writes on
+// two private cells of `spare` (34 floats per warp) instead of branching.
+constexpr int DEAD_LO = -2000;          // keys of lanes left of the row (+ lane)
+constexpr int DEAD_HI = 0x40000000;     // ... right of it, or past its end
+
+// The lanes of the warp whose key equals this lane's.  Destination columns are
+// non-decreasing along a chunk almost everywhere (they decrease only where the
+// disparity jumps by more than a pixel per pixel); equal keys are then
+// contiguous runs, found with one shuffle and two votes.  match.any -- one per
+// ~67 cycles and scheduler -- is left to the chunks that are not monotone.
+__device__ __forceinline__ unsigned equal_key_lanes(int key, int lane) {
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool first = lane == 0;
+    if (!__all_sync(0xffffffffu, first || key >= prev))
+        return __match_any_sync(0xffffffffu, key);
+    const unsigned heads = __ballot_sync(0xffffffffu, first || key != prev);
+    const unsigned upto = 0xffffffffu >> (31 - lane);        // lanes <= this one
+    const int start = 31 - __clz(heads & upto);              // head of this run
+    const unsigned later = heads & ~upto;
+    const int end = later ? __ffs(later) - 1 : 32;           // one past its last lane
+    return (0xffffffffu >> (32 - end)) & (0xffffffffu << start);
+}
+
+__device__ __forceinline__ void scatter_chunk(float* Hrow, float* spare, int d,
                                               unsigned grp, float a0, float a1,
                                               int lane) {
-    stage[lane] = make_float2(a0, a1);
-    __syncwarp();
-    const bool leader = d >= -1 && (grp & ((1u << lane) - 1u)) == 0u;
-    if (leader) {
-        // own contribution first (the leader is the lowest lane), then the
-        // rest of the group in lane order; most groups are singletons
-        float s0 = a0, s1 = a1;
-        for (unsigned m = grp & (grp - 1u); m; m &= m - 1u) {
-            const float2 c = stage[__ffs(m) - 1];
-            s0 += c.x; s1 += c.y;
-        }
-        Hrow[d] += s0;
-        a1 = s1;
+    const bool leader = d >= -1 && d < DEAD_HI && (grp & ((1u << lane) - 1u)) == 0u;
+    // own contribution first (the leader is the lowest lane), then the rest of
+    // the group in lane order; most groups are singletons
+    unsigned m = leader ? grp & (grp - 1u) : 0u;
+    float s0 = a0, s1 = a1;
+    while (__any_sync(0xffffffffu, m != 0u)) {
+        const int src = m ? __ffs(m) - 1 : lane;
+        const float t0 = __shfl_sync(0xffffffffu, a0, src);
+        const float t1 = __shfl_sync(0xffffffffu, a1, src);
+        if (m) { s0 += t0; s1 += t1; }
+        m &= m - 1u;
     }
+    float* p = leader ? Hrow + d : spare + lane;
+    p[0] += leader ? s0 : 0.0f;
     __syncwarp();
-    if (leader) Hrow[d + 1] += a1;
-    // (no barrier here: the caller alternates two staging buffers, and the
-    //  barrier after the next chunk's staging orders these updates before its)
+    p[1] += leader ? s1 : 0.0f;
+    __syncwarp();
 }
 
 // ALIGNED: every row width of the launch is a multiple of 32 (a chunk is either
@@ -85,9 +114,13 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
     float* H = reinterpret_cast<float*>(smem_raw);        // [nr][2][HW]
     float* Vall = H + (size_t)(P.R + 2) * 2 * HW;         // [nwarps][HW]
     float* Vd = Vall + (size_t)warp * HW + HPAD;
-    float* xb = Vall + (size_t)nwarps * HW;               // [w] linspace(0,1,w)
-    float2* stage = reinterpret_cast<float2*>(xb + ((w + 3) & ~3)) + warp * 64;
-    for (int x = tid; x < w; x += blockDim.x) xb[x] = linspace01(x, w);
+    // linspace(0,1,w), padded to whole spans (every lane of a span reads it)
+    float* xb = Vall + (size_t)nwarps * HW;
+    const int xbn = xb_floats(w);
+    float* spare = xb + xbn + warp * 64;
+    if (lane < 2) { spare[lane] = 0.0f; spare[32 + lane] = 0.0f; }
+    spare[2 + lane] = 0.0f;
+    for (int x = tid; x < xbn; x += blockDim.x) xb[x] = x < w ? linspace01(x, w) : 0.0f;
     __syncthreads();
     const float fw = (float)w;
 
@@ -136,24 +169,26 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
                     const bool valid = ALIGNED ? span + j * 32 < w : x < w;
                     const float a = c0[j];
                     // warp_coord(x, w, sign * a) with the base grid from the table
-                    const float g = fmaf(2.0f, xb[valid ? x : 0] + sign * a, -1.0f);
+                    const float g = fmaf(2.0f, xb[x] + sign * a, -1.0f);
                     const Tap2 tx = split_coord(fmaf(g + 1.0f, 0.5f * fw, -0.5f));
                     const int xi = min(max(tx.i0, -HPAD), w);
                     const float f0 = Vd[xi], f1 = Vd[xi + 1];
                     const float f = a - (tx.w0 * f0 + tx.w1 * f1);
-                    const float rr = k * sgnf(f);
+                    // -k * sign(f), as two selects
+                    float m = f > 0.0f ? -k : 0.0f;
+                    m = f < 0.0f ? k : m;
                     // taps -1 and w land in the pads of the row; dead lanes get
-                    // unique negative keys
-                    const bool live = valid && xi >= -1 && xi <= w - 1;
-                    dst[j] = live ? xi : -1000 - lane;
-                    c0[j] = -rr * tx.w0;
-                    c1[j] = -rr * tx.w1;
-                    grp[j] = __match_any_sync(0xffffffffu, dst[j]);
+                    // unique keys below / above every column, in lane order
+                    const bool live = valid && (unsigned)(xi + 1) <= (unsigned)w;
+                    dst[j] = live ? xi : (xi < 0 ? DEAD_LO : DEAD_HI) + lane;
+                    c0[j] = m * tx.w0;
+                    c1[j] = m * tx.w1;
+                    grp[j] = equal_key_lanes(dst[j], lane);
                 }
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     if (span + j * 32 >= w) break;
-                    scatter_chunk(Hrow, stage + (j & 1) * 32, dst[j], grp[j], c0[j], c1[j], lane);
+                    scatter_chunk(Hrow, spare, dst[j], grp[j], c0[j], c1[j], lane);
                 }
             }
         }
@@ -206,8 +241,8 @@ int cons_scatter2_launch(MultiCons* C, cudaStream_t st) {
         C->strips[k] = (c.h + c.R - 1) / c.R;
         C->cta_start[k + 1] = C->cta_start[k] + C->strips[k] * c.B;
         const size_t bytes = (((size_t)(c.R + 2) * 2 + CONS2_THREADS / 32) *
-                                  (c.w + 2 * HPAD) + ((c.w + 3) & ~3) +
-                              (size_t)CONS2_THREADS * 4) * sizeof(float);
+                                  (c.w + 2 * HPAD) + xb_floats(c.w) +
+                              (size_t)CONS2_THREADS * 2) * sizeof(float);
         if (bytes > smem) smem = bytes;
     }
     if (smem > 220 * 1024) return USL_ERR_UNSUPPORTED;
