@@ -205,6 +205,40 @@ def test_total_loss_matches_oracle(dev, loss_type, shape):
         assert r < GRAD_REL, (i, r)
 
 
+@pytest.mark.parametrize('kind', ['ramps', 'ramps_with_jumps'])
+def test_smooth_disparities_match_oracle(dev, kind):
+    """Piecewise-linear disparities: the destination columns of the transposed
+    warp are monotone along most chunks, so the scatter groups equal
+    destinations as contiguous runs (slopes < 1: runs of two and three; the
+    white-noise inputs of the other tests always take the match.any branch).
+    `ramps_with_jumps` adds disparity steps inside rows: chunks of both kinds
+    side by side."""
+    from oracle import loss_port as P
+    from oracle.make_golden import loss_config, make_inputs
+    b, h, w = 2, 64, 256
+    cfg = loss_config('bayesian', smoothness_weight=0.25)
+    left, right, preds = make_inputs(b, h, w, 0.3, 35)
+    g = torch.Generator().manual_seed(5)
+    smooth = []
+    for i, p in enumerate(preds):
+        hh, ww = p.shape[2:]
+        x = torch.linspace(0, 1, ww).view(1, 1, 1, ww)
+        y = torch.linspace(0, 1, hh).view(1, 1, hh, 1)
+        a = torch.rand(b, 4, 1, 1, generator=g)
+        q = 0.02 + 0.25 * (a * x + (1 - a) * 0.5 * y) + 0.002 * p
+        if kind == 'ramps_with_jumps':
+            q = q + 0.05 * (x > 0.37).float() - 0.04 * (x > 0.71).float()
+        smooth.append(q.contiguous())
+    stereo = torch.cat([left, right], 1)
+    rdl, rel, rgrads = P.step(stereo.double(), [p.double() for p in smooth], cfg)
+    dl, el, gp, *_ = run_ours(dev, stereo, smooth, cfg)
+    assert abs(dl.item() - float(rdl)) <= LOSS_REL * abs(float(rdl))
+    assert abs(el.item() - float(rel)) <= LOSS_REL * abs(float(rel))
+    for i in range(4):
+        r = grad_err(gp[i].grad, rgrads[i].numpy(), smooth[i])
+        assert r < GRAD_REL, (i, r)
+
+
 def test_general_strip_kernels_match_oracle(dev, monkeypatch):
     """The same training step with the column kernels switched off
     (USL_NO_COL): forward sums, two-launch backward on the general strip
