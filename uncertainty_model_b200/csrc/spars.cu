@@ -190,8 +190,26 @@ scan_digits_kernel(unsigned* __restrict__ totals) {
     t[threadIdx.x] = wbase + incl - v;
 }
 
+// The lanes of the warp whose 8-bit digit equals this lane's, from eight votes
+// (match.any issues once per ~67 cycles and scheduler: slower than the votes).
+__device__ __forceinline__ unsigned same_digit_lanes(unsigned d, bool valid) {
+    unsigned m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned v = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? v : ~v;
+    }
+    return m;
+}
+
+// One pass of the LSD sort for one tile: rank every item among the items of
+// its digit (warp by warp, in item order: the pass is stable), put the tile in
+// digit order in shared memory, and copy it out -- consecutive threads then
+// write consecutive words of a digit's run (a scattered 4-byte store per lane
+// costs a whole sector of load/store-unit time each).
 template <bool WITH_IDX>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 scatter_kernel(const unsigned* __restrict__ keys_in,
                const float* __restrict__ vals_in, const int* __restrict__ idx_in,
                unsigned* __restrict__ keys_out, float* __restrict__ vals_out,
@@ -199,6 +217,10 @@ scatter_kernel(const unsigned* __restrict__ keys_in,
                const unsigned* __restrict__ digit_base, int n, int ntiles,
                int shift) {
     __shared__ unsigned whist[SORT_WARPS][RADIX];
+    __shared__ unsigned skeys[SORT_TILE];
+    __shared__ unsigned sdata[SORT_TILE];      // payload words (values, then indices)
+    __shared__ unsigned delta[RADIX];          // global position - position in the tile
+    __shared__ unsigned wsum[SORT_WARPS];
     const int row = blockIdx.y, tile = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -206,16 +228,21 @@ scatter_kernel(const unsigned* __restrict__ keys_in,
         (&whist[0][0])[i] = 0;
     __syncthreads();
     const long long rbase = (long long)row * n;
-    const int wbase = tile * SORT_TILE + warp * WARP_SPAN;
+    const int tbase = tile * SORT_TILE;
+    const int wbase = tbase + warp * WARP_SPAN;
+    const int cnt = min(SORT_TILE, n - tbase);
     unsigned key[SORT_ITEMS];
     unsigned short rank[SORT_ITEMS];
 #pragma unroll
     for (int c = 0; c < SORT_ITEMS; ++c) {
         const int i = wbase + c * 32 + lane;
-        const bool valid = i < n;
-        key[c] = valid ? keys_in[rbase + i] : 0u;
+        key[c] = i < n ? keys_in[rbase + i] : 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < SORT_ITEMS; ++c) {
+        const bool valid = wbase + c * 32 + lane < n;
         const unsigned d = (key[c] >> shift) & 255u;
-        const unsigned grp = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
+        const unsigned grp = same_digit_lanes(d, valid);
         const unsigned prev = whist[warp][d];
         __syncwarp();
         if (valid && (__ffs(grp) - 1) == lane) whist[warp][d] = prev + __popc(grp);
@@ -223,27 +250,62 @@ scatter_kernel(const unsigned* __restrict__ keys_in,
         rank[c] = (unsigned short)(prev + __popc(grp & lt));
     }
     __syncthreads();
-    {   // digit threadIdx.x: exclusive bases over the warps of this tile
+    {   // digit threadIdx.x: exclusive bases over the warps of this tile, then
+        // over the digits (block scan); delta = where the digit's run goes
         const int d = threadIdx.x;
-        unsigned base = offsets[((long long)row * RADIX + d) * ntiles + tile] +
-                        digit_base[row * RADIX + d];
+        unsigned acc = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w) {
             const unsigned t = whist[w][d];
-            whist[w][d] = base;
-            base += t;
+            whist[w][d] = acc;
+            acc += t;
         }
+        unsigned incl = acc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned start = incl - acc;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w)
+            if (w < warp) start += wsum[w];
+        delta[d] = offsets[((long long)row * RADIX + d) * ntiles + tile] +
+                   digit_base[row * RADIX + d] - start;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) whist[w][d] += start;
     }
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < SORT_ITEMS; ++c) {
+    for (int c = 0; c < SORT_ITEMS; ++c) {      // rank -> position in the tile
         const int i = wbase + c * 32 + lane;
+        const unsigned d = (key[c] >> shift) & 255u;
+        rank[c] = (unsigned short)(whist[warp][d] + rank[c]);
         if (i < n) {
-            const unsigned d = (key[c] >> shift) & 255u;
-            const long long pos = rbase + whist[warp][d] + rank[c];
-            keys_out[pos] = key[c];
-            vals_out[pos] = vals_in[rbase + i];
-            if (WITH_IDX) idx_out[pos] = idx_in[rbase + i];
+            skeys[rank[c]] = key[c];
+            sdata[rank[c]] = __float_as_uint(vals_in[rbase + i]);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += SORT_THREADS) {
+        const unsigned k = skeys[j];
+        const long long pos = rbase + delta[(k >> shift) & 255u] + j;
+        keys_out[pos] = k;
+        vals_out[pos] = __uint_as_float(sdata[j]);
+    }
+    if (WITH_IDX) {
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < SORT_ITEMS; ++c) {
+            const int i = wbase + c * 32 + lane;
+            if (i < n) sdata[rank[c]] = (unsigned)idx_in[rbase + i];
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < cnt; j += SORT_THREADS) {
+            const long long pos = rbase + delta[(skeys[j] >> shift) & 255u] + j;
+            idx_out[pos] = (int)sdata[j];
         }
     }
 }
@@ -395,9 +457,19 @@ extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
         const dim3 pgrid(((ow + PX - 1) / PX + POOL_THREADS - 1) / POOL_THREADS, oh, rows);
         const int vo = (W % 4 == 0) && (((uintptr_t)oracle & 15) == 0);
         const int vp = (W % 4 == 0) && (((uintptr_t)predicted & 15) == 0);
-        pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], nullptr);
-        pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(predicted, H, W, k, vp,
-                                                        pooled_pred_out, keys[0]);
+        if (predicted == oracle) {
+            // the oracle curve (evaluate.py:155: curve(error, error)) ranks the
+            // map by itself: one pooling pass yields payload and keys
+            pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], keys[0]);
+            if (pooled_pred_out &&
+                cudaMemcpyAsync(pooled_pred_out, vals[0], (size_t)rows * n * 4,
+                                cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+                return USL_ERR_CUDA;
+        } else {
+            pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], nullptr);
+            pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(predicted, H, W, k, vp,
+                                                            pooled_pred_out, keys[0]);
+        }
     }
     if (pooled_oracle_out)
         if (cudaMemcpyAsync(pooled_oracle_out, vals[0], (size_t)rows * n * 4,
