@@ -113,3 +113,58 @@ def test_random_curve_and_errors(dev):
         S.curve(err.cpu(), err.cpu())
     with pytest.raises(ValueError):
         S.curve(err[:, :, :8, :8], err[:, :, :8, :8])
+
+
+def test_evaluation_front_half_matches_oracle(dev):
+    """The evaluation loop up to its metrics (reference evaluate.py:136-160,
+    SURVEY.md section 8f n1): split the prediction, reconstruct both views,
+    `WeightedSSIMLoss(alpha=1).image_error`, the (identity) align-corners
+    resize, then oracle / predicted / random curves, AUSE and AURG -- through
+    the drop-in modules on the GPU against the CPU oracle ports of the same
+    lines.  The error maps agree to float rounding, so the GPU curves are
+    compared (a) bit-exactly with the canonical oracle fed the GPU error map
+    and (b) to tolerance with the all-CPU flow."""
+    from oracle import loss_port as P
+    from oracle import spars_port as SP
+    from oracle.make_golden import make_inputs
+    from uncertainty_model_b200.train import loss as L
+    from uncertainty_model_b200.train import sparsification as S
+    from uncertainty_model_b200.train import utils as U
+    left, right, preds = make_inputs(2, 48, 96, 0.3, 77)
+    prediction = preds[0]
+    images = torch.cat([left, right], 1)
+
+    # reference flow, CPU oracle
+    disparity, uncertainty = torch.split(prediction, [2, 2], dim=1)
+    dl, dr = torch.split(disparity, [1, 1], dim=1)
+    recon_ref = torch.cat((P.warp_to_left(dl, right), P.warp_to_right(dr, left)), 1)
+    err_ref = P.image_error(images, recon_ref, alpha=1.0)
+    oc_ref = SP.curve_canonical(err_ref.numpy(), err_ref.numpy())
+    pc_ref = SP.curve_canonical(err_ref.numpy(), uncertainty.contiguous().numpy())
+
+    # the same lines through the drop-in modules
+    g_images, g_pred = images.to(dev), prediction.to(dev)
+    g_disp, g_unc = torch.split(g_pred, [2, 2], dim=1)
+    g_dl, g_dr = torch.split(g_disp, [1, 1], dim=1)
+    g_left, g_right = left.to(dev), right.to(dev)
+    recon = torch.cat((U.reconstruct_left_image(g_dl, g_right),
+                       U.reconstruct_right_image(g_dr, g_left)), dim=1)
+    assert np.allclose(recon.cpu().numpy(), recon_ref.numpy(), atol=2e-6)
+    error = L.WeightedSSIMLoss(alpha=1).image_error(g_images, recon)
+    assert error.shape == (2, 2, 48, 96)
+    assert np.allclose(error.cpu().numpy(), err_ref.numpy(), atol=1e-5)
+    oc = S.curve(error, error, device=dev)
+    pc = S.curve(error, g_unc, device=dev)
+    rc = S.random_curve(error, device=dev)
+    ause, aurg = S.ause(oc, pc), S.aurg(pc, rc)
+
+    e_np = error.cpu().numpy()
+    u_np = g_unc.contiguous().cpu().numpy()
+    assert np.array_equal(oc.cpu().numpy(), SP.curve_canonical(e_np, e_np))
+    assert np.array_equal(pc.cpu().numpy(), SP.curve_canonical(e_np, u_np))
+    assert np.allclose(oc.cpu().numpy(), oc_ref, rtol=1e-4)
+    assert np.allclose(pc.cpu().numpy(), pc_ref, rtol=1e-3, atol=1e-5)
+    assert np.float32(ause.item()) == SP.ause_canonical(
+        oc.cpu().numpy(), pc.cpu().numpy())
+    assert np.isfinite(aurg.item()) and rc.shape == (100,)
+    assert bool((oc <= pc + 1e-6).all())
