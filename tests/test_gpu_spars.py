@@ -168,3 +168,22 @@ def test_evaluation_front_half_matches_oracle(dev):
         oc.cpu().numpy(), pc.cpu().numpy())
     assert np.isfinite(aurg.item()) and rc.shape == (100,)
     assert bool((oc <= pc + 1e-6).all())
+
+
+@pytest.mark.parametrize('k', [3, 7, 15])
+def test_other_kernel_sizes_bit_exact(dev, k):
+    """Window sizes other than the default 11 run the run-time-size pooling
+    kernel; pooled maps and curves stay bit-exact against the canonical oracle
+    (ragged shape: neither dimension a multiple of the thread patch)."""
+    from oracle import spars_port as SP
+    from uncertainty_model_b200.train import sparsification as S
+    err, unc = SP.synthetic_maps(2, 37, 61, seed=3 + k)
+    acc, rows, parts = S.curve_sums(err.to(dev), unc.to(dev), kernel_size=k,
+                                    return_order=True)
+    e, u = err.numpy(), unc.numpy()
+    pe = SP.pool_exact(e, k).reshape(2, 2, -1)
+    pu = SP.pool_exact(u, k).reshape(2, 2, -1)
+    assert np.array_equal(parts['pooled_oracle'].cpu().numpy().reshape(2, 2, -1), pe)
+    assert np.array_equal(parts['pooled_pred'].cpu().numpy().reshape(2, 2, -1), pu)
+    pc = S.curve(err.to(dev), unc.to(dev), kernel_size=k, device=dev)
+    assert np.array_equal(pc.cpu().numpy(), SP.curve_canonical(e, u, k))

@@ -46,31 +46,42 @@ __device__ __forceinline__ unsigned desc_key(float v) {
 }
 
 // ---- pool ---------------------------------------------------------------
-// grid (column groups, output rows, maps).  Each thread produces PX horizontally
-// adjacent outputs, so a window row is loaded once -- as 128-bit loads where the
-// row allows it (the loads of a warp then cover one contiguous span: this
-// kernel is bound by L1 wavefronts otherwise) -- and feeds PX accumulators;
-// every accumulator still adds its k*k values one by one in row-major order.
+// grid (column groups, blocks of PY output rows, maps).  Each thread produces a
+// PX x PY patch of outputs, so a window row is loaded once -- as 128-bit loads
+// where the row allows it (the loads of a warp then cover one contiguous span:
+// this kernel is bound by L1 wavefronts otherwise) -- and feeds the PX
+// accumulators of every output row whose window holds it; every accumulator
+// still adds its k*k values one by one in row-major order (input rows arrive in
+// increasing order, so each output row sees its window rows in order).
 constexpr int PX = 8;
+constexpr int PY = 4;
 constexpr int KMAX = 15;
 constexpr int POOL_THREADS = 128;
 constexpr int PV = (KMAX + PX - 1 + 3) / 4 * 4;     // values held per window row
 
+// K: the window size when it is known at compile time (11, the reference's
+// default: no predicated-off adds), 0 = the run-time `kk` (any size to KMAX).
+template <int K>
 __global__ void __launch_bounds__(POOL_THREADS)
-pool_kernel(const float* __restrict__ in, int H, int W, int k, int vec_ok,
+pool_kernel(const float* __restrict__ in, int H, int W, int kk, int vec_ok,
             float* __restrict__ out_val, unsigned* __restrict__ out_key) {
+    const int k = K ? K : kk;
     const int oh = H - k + 1, ow = W - k + 1;
     const int ox = (blockIdx.x * POOL_THREADS + threadIdx.x) * PX;
     if (ox >= ow) return;
-    const int oy = blockIdx.y, row = blockIdx.z;
+    const int oy0 = blockIdx.y * PY, row = blockIdx.z;
+    const int ny = min(PY, oh - oy0);               // output rows of this patch
     const float div = (float)(k * k);
-    const float* p = in + ((long long)row * H + oy) * W + ox;
+    const float* p = in + ((long long)row * H + oy0) * W + ox;
     const int need = k + PX - 1;
     const bool vec = vec_ok && ox + ((need + 3) & ~3) <= W;
-    float acc[PX];
+    constexpr int KU = K ? K : KMAX;                // unrolled window columns
+    float acc[PY][PX];
 #pragma unroll
-    for (int j = 0; j < PX; ++j) acc[j] = 0.0f;
-    for (int dy = 0; dy < k; ++dy) {
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
+        for (int j = 0; j < PX; ++j) acc[r][j] = 0.0f;
+    for (int y = 0; y < ny + k - 1; ++y) {          // input row oy0 + y
         float v[PV];
         if (vec) {
 #pragma unroll
@@ -85,22 +96,30 @@ pool_kernel(const float* __restrict__ in, int H, int W, int k, int vec_ok,
                 v[j] = (j < need && ox + j < W) ? __ldg(p + j) : 0.0f;
         }
 #pragma unroll
-        for (int dx = 0; dx < KMAX; ++dx)
-            if (dx < k) {
+        for (int r = 0; r < PY; ++r) {
+            if (y - r < 0 || y - r >= k || r >= ny) continue;   // (uniform)
 #pragma unroll
-                for (int j = 0; j < PX; ++j)
-                    acc[j] = __fadd_rn(acc[j], v[dx + j]);
-            }
+            for (int dx = 0; dx < KU; ++dx)
+                if (K || dx < k) {
+#pragma unroll
+                    for (int j = 0; j < PX; ++j)
+                        acc[r][j] = __fadd_rn(acc[r][j], v[dx + j]);
+                }
+        }
         p += W;
     }
-    const long long o = ((long long)row * oh + oy) * ow + ox;
 #pragma unroll
-    for (int j = 0; j < PX; ++j)
-        if (ox + j < ow) {
-            const float m = __fdiv_rn(acc[j], div);
-            if (out_val) out_val[o + j] = m;
-            if (out_key) out_key[o + j] = desc_key(m);
-        }
+    for (int r = 0; r < PY; ++r) {
+        if (r >= ny) break;
+        const long long o = ((long long)row * oh + oy0 + r) * ow + ox;
+#pragma unroll
+        for (int j = 0; j < PX; ++j)
+            if (ox + j < ow) {
+                const float m = __fdiv_rn(acc[r][j], div);
+                if (out_val) out_val[o + j] = m;
+                if (out_key) out_key[o + j] = desc_key(m);
+            }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -123,10 +142,26 @@ hist_kernel(const unsigned* __restrict__ keys, int n, int ntiles, int shift,
     __syncthreads();
     const unsigned* k = keys + (long long)row * n;
     const int base = tile * SORT_TILE;
+    if (base + SORT_TILE <= n && (((uintptr_t)(k + base)) & 15) == 0) {
+        // whole, 16-byte aligned tile: four 128-bit loads per thread (the order
+        // of the items does not matter to a histogram)
+        const uint4* k4 = reinterpret_cast<const uint4*>(k + base);
+        uint4 v[SORT_ITEMS / 4];
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) {
-        const int i = base + j * SORT_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(k[i] >> shift) & 255u], 1u);   // integer: exact
+        for (int j = 0; j < SORT_ITEMS / 4; ++j) v[j] = __ldg(k4 + j * SORT_THREADS + threadIdx.x);
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS / 4; ++j) {
+            atomicAdd(&h[(v[j].x >> shift) & 255u], 1u);   // integer: exact
+            atomicAdd(&h[(v[j].y >> shift) & 255u], 1u);
+            atomicAdd(&h[(v[j].z >> shift) & 255u], 1u);
+            atomicAdd(&h[(v[j].w >> shift) & 255u], 1u);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; ++j) {
+            const int i = base + j * SORT_THREADS + threadIdx.x;
+            if (i < n) atomicAdd(&h[(k[i] >> shift) & 255u], 1u);
+        }
     }
     __syncthreads();
     counts[((long long)row * RADIX + threadIdx.x) * ntiles + tile] = h[threadIdx.x];
@@ -454,21 +489,23 @@ extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
     {
         const int oh = H - k + 1, ow = W - k + 1;
         if (oh > 65535 || rows > 65535) return USL_ERR_UNSUPPORTED;
-        const dim3 pgrid(((ow + PX - 1) / PX + POOL_THREADS - 1) / POOL_THREADS, oh, rows);
+        const dim3 pgrid(((ow + PX - 1) / PX + POOL_THREADS - 1) / POOL_THREADS,
+                         (oh + PY - 1) / PY, rows);
         const int vo = (W % 4 == 0) && (((uintptr_t)oracle & 15) == 0);
         const int vp = (W % 4 == 0) && (((uintptr_t)predicted & 15) == 0);
+        auto pool = k == 11 ? pool_kernel<11> : pool_kernel<0>;
         if (predicted == oracle) {
             // the oracle curve (evaluate.py:155: curve(error, error)) ranks the
             // map by itself: one pooling pass yields payload and keys
-            pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], keys[0]);
+            pool<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], keys[0]);
             if (pooled_pred_out &&
                 cudaMemcpyAsync(pooled_pred_out, vals[0], (size_t)rows * n * 4,
                                 cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
                 return USL_ERR_CUDA;
         } else {
-            pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], nullptr);
-            pool_kernel<<<pgrid, POOL_THREADS, 0, stream>>>(predicted, H, W, k, vp,
-                                                            pooled_pred_out, keys[0]);
+            pool<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], nullptr);
+            pool<<<pgrid, POOL_THREADS, 0, stream>>>(predicted, H, W, k, vp,
+                                                     pooled_pred_out, keys[0]);
         }
     }
     if (pooled_oracle_out)
