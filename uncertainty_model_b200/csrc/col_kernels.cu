@@ -70,7 +70,19 @@ int col_plan(ColPlan* M, bool grad) {
             if (want_strips < 1) want_strips = 1;
             wantR = (p.h + want_strips - 1) / want_strips;
             if (wantR < 32) wantR = 32;
-            if (wantR > 128) wantR = 128;       // (per-step tables live in shared memory)
+            if (wantR > 128) {
+                // one wave on 70 % of the SMs would need taller strips than the
+                // per-step tables in shared memory allow: several waves on all
+                // SMs, as few strip steps (rows + 8 of halo) in total as possible
+                int best = 128, best_cost = 0x7fffffff;
+                for (int s = (p.h + 127) / 128; s <= (p.h + 31) / 32; ++s) {
+                    const int R = (p.h + s - 1) / s;
+                    const int waves = (per_strip * s + num_sms() - 1) / num_sms();
+                    const int cost = waves * (R + 8);
+                    if (cost < best_cost) { best_cost = cost; best = R; }
+                }
+                wantR = best;
+            }
         }
         int strips = (p.h + wantR - 1) / wantR;
         int R = (((p.h + strips - 1) / strips) + 1) & ~1;
