@@ -39,7 +39,8 @@ bool col_eligible(const UslLossConfig* cfgs, const UslLossScale* scales, int n) 
     return true;
 }
 
-int col_plan(ColPlan* M, bool grad) {
+// The plan with a given minimum strip height.
+static int col_plan_floor(ColPlan* M, bool grad, int floorR) {
     const int maxT = COL_MAX_THREADS;
     // widest two-view unit (in threads): wider rows get one unit per view
     const int maxT2 = env_int3("USL_COL_MAXT2", COL_MAX_THREADS);
@@ -47,7 +48,7 @@ int col_plan(ColPlan* M, bool grad) {
     // SM each (registers); the other scales run beside them only on the SMs
     // they leave free.  Measured best (profiles/, config 2): the largest scale
     // on ~2/3 of the SMs in ONE wave, 32-row strips below.
-    const int R0 = env_int3("USL_COL_R0", 0), R1 = env_int3("USL_COL_R", 32);
+    const int R0 = env_int3("USL_COL_R0", 0), R1 = env_int3("USL_COL_R", floorR);
     long long rows = 0;
     for (int i = 0; i < M->n; ++i) {
         LossParams& p = M->P[i];
@@ -69,7 +70,7 @@ int col_plan(ColPlan* M, bool grad) {
             int want_strips = (7 * num_sms() / 10) / per_strip;
             if (want_strips < 1) want_strips = 1;
             wantR = (p.h + want_strips - 1) / want_strips;
-            if (wantR < 32) wantR = 32;
+            if (wantR < floorR) wantR = floorR;
             if (wantR > 128) {
                 // one wave on 70 % of the SMs would need taller strips than the
                 // per-step tables in shared memory allow: several waves on all
@@ -110,6 +111,19 @@ int col_plan(ColPlan* M, bool grad) {
     }
     M->row_start[M->n] = (int)rows;
     return USL_OK;
+}
+
+int col_plan(ColPlan* M, bool grad) {
+    // Strips of at least 32 rows (8 more rows of halo work each) -- unless the
+    // whole step then has so few units that most SMs stay idle (small batches):
+    // halve the minimum while all the units still fit on the SMs at once, the
+    // step is as long as its longest unit.
+    int rc = col_plan_floor(M, grad, 32);
+    for (int floorR = 16; rc == USL_OK && floorR >= 8; floorR /= 2) {
+        if (2 * M->row_start[M->n] > num_sms()) break;
+        rc = col_plan_floor(M, grad, floorR);
+    }
+    return rc;
 }
 
 template <int CLS>

@@ -231,12 +231,20 @@ cons_scatter2_kernel(const __grid_constant__ MultiCons M) {
 }
 
 int cons_scatter2_launch(MultiCons* C, cudaStream_t st) {
-    // strips of 14 destination rows: 2 * 16 jobs over 16 warps, two CTAs per SM
+    // strips of 14 destination rows: 2 * 16 jobs over 16 warps, two CTAs per
+    // SM -- or of 6 rows (one job per warp, half as long a CTA) when even those
+    // all run at once (small batches: the step is as long as one CTA)
     size_t smem = 0;
+    int R = CONS2_R;
+    {
+        long long ctas = 0;
+        for (int k = 0; k < C->n; ++k) ctas += (long long)((C->P[k].h + 5) / 6) * C->P[k].B;
+        if (ctas <= 2 * num_sms()) R = 6;
+    }
     C->cta_start[0] = 0;
     for (int k = 0; k < C->n; ++k) {
         ConsParams& c = C->P[k];
-        c.R = CONS2_R;
+        c.R = R;
         if (c.R > c.h) c.R = c.h;
         C->strips[k] = (c.h + c.R - 1) / c.R;
         C->cta_start[k + 1] = C->cta_start[k] + C->strips[k] * c.B;
