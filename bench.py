@@ -405,7 +405,8 @@ def run_ours(args, rank, world, local_rank):
 
 def kernel_times(K, U, fn, sets, dev, reps):
     """Average duration of each kernel of the step, launched alone, measured
-    with CUDA events on the launching stream, inputs rotating over the sets."""
+    with CUDA events on the launching stream, inputs rotating over the sets
+    (> L2 in total)."""
     st = fn._settings()
     nsets = len(sets)
     prepared = []
@@ -429,15 +430,36 @@ def kernel_times(K, U, fn, sets, dev, reps):
     one = torch.ones((), device=dev)
 
     def t(fnc):
-        for i in range(3):
+        """Mean device time of fnc(i): one CUDA graph per input set, each
+        replay between two events on the launching stream (eager calls put the
+        host's launch gaps between the four concurrent per-scale launches into
+        the number); eager if the call cannot be captured."""
+        for i in range(max(3, nsets)):
             fnc(i)
         torch.cuda.synchronize()
+        graphs = []
+        try:
+            for i in range(nsets):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fnc(i)
+                graphs.append(g)
+        except Exception:
+            graphs = None
+            torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        if graphs:
+            for g in graphs:
+                g.replay()
+            torch.cuda.synchronize()
         total = 0.0
-        for i in range(reps):
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
+        for i in range(reps):       # one launch at a time: "launched alone"
             e0.record()
-            fnc(i)
+            if graphs:
+                graphs[i % nsets].replay()
+            else:
+                fnc(i)
             e1.record()
             e1.synchronize()
             total += e0.elapsed_time(e1)

@@ -157,11 +157,22 @@ int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st) {
         }
         return USL_OK;
     }
-    // fork: what precedes on `st` (the scatter kernel) is ordered before every
-    // scale; scale 0 stays on `st` and is launched first
+    // fork: what precedes on `st` is ordered before every scale.  Scale 0 goes
+    // to the high-priority stream: when all four launches become ready at the
+    // same moment (graph replay) its CTAs -- a whole SM each, the longest of
+    // the step -- must be placed first, not behind the small scales' CTAs.
     if (cudaEventRecord(pool->fork, st) != cudaSuccess) return USL_ERR_CUDA;
-    const bool small_first = getenv("USL_COL_SMALL_FIRST") != nullptr;
-    int rc = small_first ? USL_OK : col_launch_scale(M, 0, grad, skip_if_unit, st);
+    const bool hi = !getenv("USL_COL_NO_PRIORITY");
+    int rc = USL_OK;
+    if (hi) {
+        if (cudaStreamWaitEvent(pool->first, pool->fork, 0) != cudaSuccess) return USL_ERR_CUDA;
+        rc = col_launch_scale(M, 0, grad, skip_if_unit, pool->first);
+        if (cudaEventRecord(pool->join_first, pool->first) != cudaSuccess ||
+            cudaStreamWaitEvent(st, pool->join_first, 0) != cudaSuccess)
+            rc = rc == USL_OK ? USL_ERR_CUDA : rc;
+    } else {
+        rc = col_launch_scale(M, 0, grad, skip_if_unit, st);
+    }
     for (int i = 1; i < M->n && rc == USL_OK; ++i) {
         cudaStream_t s = pool->side[i - 1];
         if (cudaStreamWaitEvent(s, pool->fork, 0) != cudaSuccess) { rc = USL_ERR_CUDA; break; }
@@ -171,7 +182,6 @@ int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st) {
             cudaStreamWaitEvent(st, pool->join[i - 1], 0) != cudaSuccess)
             rc = rc == USL_OK ? USL_ERR_CUDA : rc;
     }
-    if (small_first && rc == USL_OK) rc = col_launch_scale(M, 0, grad, skip_if_unit, st);
     return rc;
 }
 

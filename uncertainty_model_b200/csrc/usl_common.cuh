@@ -31,11 +31,14 @@ inline int num_sms() {
 // caller's stream: one small pool per host thread and device, created on first
 // use and never destroyed (immutable afterwards; nothing is shared between
 // host threads).  side[0 .. USL_MAX_SCALES-2]: per-scale launches of the fused
-// kernel; side[USL_MAX_SCALES-1]: the scatter kernel.
+// kernel; `first`: a stream of the highest priority for the launch whose CTAs
+// must be placed before those of the others (the largest scale's: each takes
+// a whole SM, and the step is as long as they are).
 struct StreamPool {
     bool ready = false, failed = false;
     cudaStream_t side[USL_MAX_SCALES];
-    cudaEvent_t fork, fork2, join[USL_MAX_SCALES];
+    cudaStream_t first;
+    cudaEvent_t fork, fork2, join[USL_MAX_SCALES], join_first;
 };
 inline StreamPool* stream_pool() {
     constexpr int MAX_DEV = 64;
@@ -45,7 +48,11 @@ inline StreamPool* stream_pool() {
     StreamPool& p = pools[dev];
     if (p.failed) return nullptr;
     if (!p.ready) {
-        bool ok = cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess &&
+        int lo = 0, hi = 0;
+        bool ok = cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&p.first, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&p.join_first, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&p.fork2, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < USL_MAX_SCALES; ++i)
             ok = cudaStreamCreateWithFlags(&p.side[i], cudaStreamNonBlocking) == cudaSuccess &&
