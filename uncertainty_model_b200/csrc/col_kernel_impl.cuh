@@ -172,7 +172,8 @@ int col_launch_class(const ColPlan* M, int i, bool grad, int skip_if_unit,
         USL_COL_GO(false, MODE_MASKED, -1);
     }
     if constexpr (CLS == COL_MAX_THREADS) {      // column tiles: widest class only
-        if (grad) USL_COL_GO(true, MODE_TILED, -1);
+        if (grad) { if (hot) USL_COL_GO(true, MODE_TILED, COL_HOT_TERMS); USL_COL_GO(true, MODE_TILED, -1); }
+        if (hot) USL_COL_GO(false, MODE_TILED, COL_HOT_TERMS);
         USL_COL_GO(false, MODE_TILED, -1);
     }
 #undef USL_COL_GO
