@@ -549,14 +549,16 @@ USL_HD void c_pV(const LossParams& P, const CGeo& G, const CRings& S, int r,
         const bool ok1 = ty.i0 + 1 >= 0 && ty.i0 + 1 < P.h;
         const unsigned r0 = (unsigned)((ok0 ? ty.i0 : ty.i0 + 1) * P.w);
         const unsigned r1 = (unsigned)((ok1 ? ty.i0 + 1 : ty.i0) * P.w);
-        for (int it = tid; it < G.nv * P.w; it += nt) {
-            const int vi = it / P.w, x = it - vi * P.w;
-            const int v = G.v0 + vi;
-            const float* im = P.img + (unsigned)((long long)G.b * P.img_bs +
-                                                 (long long)(1 - v) * 3 * P.img_cs + x);
-            const float* pd = P.disp + (unsigned)((long long)G.b * P.d_bs +
-                                                  (long long)(1 - v) * P.d_cs + x);
-            st_f4(S.V + (size_t)vi * (P.w + 2 * VPAD) + VPAD + x,
+        // (column-tiled units hold one view: col_plan)
+        const int v = G.v0;
+        const float* im0 = P.img + (unsigned)((long long)G.b * P.img_bs +
+                                              (long long)(1 - v) * 3 * P.img_cs);
+        const float* pd0 = P.disp + (unsigned)((long long)G.b * P.d_bs +
+                                               (long long)(1 - v) * P.d_cs);
+        for (int x = tid; x < P.w; x += nt) {
+            const float* im = im0 + x;
+            const float* pd = pd0 + x;
+            st_f4(S.V + VPAD + x,
                   t.w0 * USL_LDG(im + r0) + t.w1 * USL_LDG(im + r1),
                   t.w0 * USL_LDG(im + P.img_cs + r0) + t.w1 * USL_LDG(im + P.img_cs + r1),
                   t.w0 * USL_LDG(im + 2 * P.img_cs + r0) + t.w1 * USL_LDG(im + 2 * P.img_cs + r1),
