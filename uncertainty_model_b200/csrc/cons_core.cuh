@@ -12,8 +12,9 @@
 //     H(y'+1) in fixed order with the row weights;
 //   * the horizontal scatter of one row is done by ONE warp walking the row in
 //     32-column chunks, in order.  Within a chunk lanes with the same
-//     destination are grouped with match.any, summed by the group leader in
-//     lane order, and the leaders -- whose destinations are now unique -- do
+//     destination are grouped (runs of a monotone chunk, else match.any),
+//     summed by the group leader in lane order, and the leaders -- whose
+//     destinations are now unique -- do
 //     plain shared-memory read-modify-writes (first tap, __syncwarp, second
 //     tap).  No atomics; the summation order is a pure function of the data.
 //

@@ -36,16 +36,6 @@ __host__ __device__ inline int xb_floats(int w) {
     return (w + 32 * NCH - 1) / (32 * NCH) * (32 * NCH);
 }
 
-// One chunk of 32 sources into H.  `d`: destination column of the first tap
-// (dead lanes: a unique key below -1 or from DEAD_HI up; they write nothing).  Lanes that share a
-// destination form a group (`grp`, from match.any -- issued by the caller for a
-// whole span at once: the unit is slow and its latency long).  Each group
-// LEADER -- its lowest lane -- adds up the contributions of its group in lane
-// order, fetched with shuffles in a loop every lane walks together (its trip
-// count is the size of the largest group, minus one: no divergent branches);
-// then the leaders, whose destinations are distinct, update H: first taps,
-// __syncwarp, second taps.  The other lanes do the same read-modify-writes on
-// two private cells of `spare` (34 floats per warp) instead of branching.
 constexpr int DEAD_LO = -2000;          // keys of lanes left of the row (+ lane)
 constexpr int DEAD_HI = 0x40000000;     // ... right of it, or past its end
 
@@ -67,6 +57,17 @@ __device__ __forceinline__ unsigned equal_key_lanes(int key, int lane) {
     return (0xffffffffu >> (32 - end)) & (0xffffffffu << start);
 }
 
+// One chunk of 32 sources into H.  `d`: destination column of the first tap
+// (dead lanes: a unique key below -1 or from DEAD_HI up; they write nothing).
+// Lanes that share a destination form a group (`grp`, from equal_key_lanes --
+// issued by the caller for a whole span at once: match.any is slow and its
+// latency long).  Each group LEADER -- its lowest lane -- adds up the
+// contributions of its group in lane order, fetched with shuffles in a loop
+// every lane walks together (its trip count is the size of the largest group,
+// minus one: no divergent branches); then the leaders, whose destinations are
+// distinct, update H: first taps, __syncwarp, second taps.  The other lanes do
+// the same read-modify-writes on two private cells of `spare` (34 floats per
+// warp) instead of branching.
 __device__ __forceinline__ void scatter_chunk(float* Hrow, float* spare, int d,
                                               unsigned grp, float a0, float a1,
                                               int lane) {
