@@ -495,7 +495,21 @@ USL_HD void c_ring_issue(const LossParams& P, const CGeo& G, const CRings& S,
              S.isrc[lane] + (long long)row * P.w, bytes, bar);
 }
 
-// MODE_MASKED / MODE_TILED: every thread moves its own column (plain loads).
+// MODE_MASKED / MODE_TILED: every thread moves its own column -- with
+// asynchronous 4-byte copies (cp.async: no register, nothing waits here); the
+// step waits for them (c_fill_wait) right before the block barrier that
+// precedes the first read of the row, one P1 later.
+#if defined(__CUDA_ARCH__)
+USL_HD void cp_f32(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src)
+                 : "memory");
+}
+USL_HD void c_fill_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else
+USL_HD void cp_f32(float* dst, const float* src) { *dst = *src; }
+USL_HD void c_fill_wait() {}
+#endif
+
 template <int SROW, int MODE>
 USL_HD void c_ring_fill(const LossParams& P, const CGeo& G, const CState& T, int row) {
     if (!T.active || row < 0 || row >= P.h) return;
@@ -503,18 +517,18 @@ USL_HD void c_ring_fill(const LossParams& P, const CGeo& G, const CState& T, int
     const unsigned ro = (unsigned)(row * P.w);
     float* dst = T.sb + (ROW_IN + slot * NPL) * SROW;
     const float* im = P.img + (T.o_img + ro);
-    dst[0] = USL_LDG(im);
-    dst[SROW] = USL_LDG(im + P.img_cs);
-    dst[2 * SROW] = USL_LDG(im + 2 * P.img_cs);
-    dst[3 * SROW] = USL_LDG(P.disp + (T.o_d + ro));
-    if (P.unc) dst[4 * SROW] = USL_LDG(P.unc + (T.o_u + ro));
+    cp_f32(dst, im);
+    cp_f32(dst + SROW, im + P.img_cs);
+    cp_f32(dst + 2 * SROW, im + 2 * P.img_cs);
+    cp_f32(dst + 3 * SROW, P.disp + (T.o_d + ro));
+    if (P.unc) cp_f32(dst + 4 * SROW, P.unc + (T.o_u + ro));
     if (MODE != MODE_TILED && G.nv == 1) {
         float* od = T.sb + (ROW_OPP + slot * NPL) * SROW;
         const float* oi = P.img + (T.o_oi + ro);
-        od[0] = USL_LDG(oi);
-        od[SROW] = USL_LDG(oi + P.img_cs);
-        od[2 * SROW] = USL_LDG(oi + 2 * P.img_cs);
-        od[3 * SROW] = USL_LDG(P.disp + (T.o_od + ro));
+        cp_f32(od, oi);
+        cp_f32(od + SROW, oi + P.img_cs);
+        cp_f32(od + 2 * SROW, oi + 2 * P.img_cs);
+        cp_f32(od + 3 * SROW, P.disp + (T.o_od + ro));
     }
 }
 

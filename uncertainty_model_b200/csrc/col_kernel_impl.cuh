@@ -28,6 +28,7 @@ template <class C, int PAR>
 __device__ __forceinline__ void col_step(const LossParams& P, const CGeo& G,
                                          const CRings& S, int r, int r_last,
                                          int ring_last, CState& T) {
+    if (C::MODE != MODE_PLAIN) c_fill_wait();   // row r+2, requested a step ago
     __syncthreads();
     c_p2<C, PAR>(P, G, S, r, T);
     if (C::STEADY || r + 1 <= r_last)
@@ -96,6 +97,7 @@ col_kernel(const __grid_constant__ ColArgs A) {
     } else {
         for (int row = r0 - 1; row <= r0 + 2 && row <= ring_last; ++row)
             c_ring_fill<SROW, MODE>(P, G, T, row);
+        c_fill_wait();
         __syncthreads();
     }
     c_pV<SROW, MODE, false>(P, G, S, r0 - 1, tid, blockDim.x, T);
