@@ -578,6 +578,19 @@ USL_HD void c_pV(const LossParams& P, const CGeo& G, const CRings& S, int r,
                   t.w0 * USL_LDG(im + 2 * P.img_cs + r0) + t.w1 * USL_LDG(im + 2 * P.img_cs + r1),
                   t.w0 * USL_LDG(pd + r0) + t.w1 * USL_LDG(pd + r1));
         }
+#if defined(__CUDA_ARCH__)
+        // the row the next step adds to this blend: ask for it now (one
+        // request per 32-byte sector), so that its loads hit L1 then
+        if (ty.i0 + 2 < P.h) {
+            const unsigned rn2 = r1 + (unsigned)P.w;
+            for (int x = tid * 8; x < P.w; x += nt * 8) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(im0 + x + rn2));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(im0 + P.img_cs + x + rn2));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(im0 + 2 * P.img_cs + x + rn2));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pd0 + x + rn2));
+            }
+        }
+#endif
     }
 }
 
