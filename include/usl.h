@@ -14,8 +14,11 @@
  *   - image-like tensors are NCHW with contiguous h*w planes; `*_bs` / `*_cs`
  *     are the batch / channel strides in elements, so channel slices of a
  *     larger tensor (prediction[:, :2]) are passed without a copy;
- *   - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises
- *     the host;
+ *   - all work is enqueued on `stream` (a cudaStream_t of the device that owns
+ *     the tensors); nothing synchronises the host.  The tensors need not live
+ *     on the caller's current device: every call makes their device current
+ *     for its duration and restores the caller's (the reference's DDP launcher
+ *     never calls torch.cuda.set_device, parallel_main.py:152-160);
  *   - return value: USL_OK or a negative UslError; never throws, never exits.
  *   - re-entrant: no global mutable state.
  */

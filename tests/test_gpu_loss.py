@@ -474,3 +474,37 @@ def test_errors(dev):
     with pytest.raises(TypeError):
         U.scale_pyramid(torch.rand(1, 6, 16, 16, dtype=torch.float64,
                                    device=dev), 2)
+
+
+def test_tensors_on_a_device_that_is_not_current(dev):
+    """The reference's DDP launcher moves model, loss and data `.to(cuda:i)`
+    and never calls torch.cuda.set_device (parallel_main.py:152-160): every
+    rank but the first runs with tensors on a device that is not the current
+    one.  The library launches where its tensors live (DeviceGuard in the C
+    ABI) and leaves the caller's current device alone; results are bit-identical
+    to the run on cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from oracle.make_golden import loss_config, make_inputs
+    from oracle import spars_port as SP
+    from uncertainty_model_b200.train import sparsification as S
+    cfg = loss_config('bayesian', smoothness_weight=0.25)
+    left, right, preds = make_inputs(2, 64, 128, 0.3, 91)
+    stereo = torch.cat([left, right], 1)
+    outs = []
+    for name in ('cuda:0', 'cuda:1'):
+        d = torch.device(name)
+        assert torch.cuda.current_device() == 0
+        dl, el, gp, pyr, rec, fn = run_ours(d, stereo, preds, cfg)
+        e_map, u_map = SP.synthetic_maps(1, 40, 56, seed=2)
+        curve = S.curve(e_map.to(d), u_map.to(d), device=d)
+        torch.cuda.synchronize(d)
+        assert torch.cuda.current_device() == 0
+        assert dl.device == d and gp[0].grad.device == d
+        outs.append((dl.item(), el.item(),
+                     [g.grad.cpu().numpy() for g in gp],
+                     [p.cpu().numpy() for p in pyr], curve.cpu().numpy()))
+    a, b = outs
+    assert a[0] == b[0] and a[1] == b[1]
+    for x, y in zip(a[2] + a[3] + [a[4]], b[2] + b[3] + [b[4]]):
+        assert np.array_equal(x, y)

@@ -290,6 +290,7 @@ extern "C" int usl_loss_plan(const UslLossConfig* cfgs,
                              const UslLossScale* scales, int n_scales,
                              int mode, int* cta_starts) {
     if (!cfgs || !scales || !cta_starts) return USL_ERR_ARG;
+    DeviceGuard guard(n_scales > 0 ? scales[0].images : nullptr);
     if (mode != USL_MODE_FWD && mode != USL_MODE_GRAD) return USL_ERR_ARG;
     if (col_eligible(cfgs, scales, n_scales)) {
         ColPlan M;
@@ -360,6 +361,7 @@ extern "C" int usl_loss_fwd(const UslLossConfig* cfgs,
                             const UslLossScale* scales, int n_scales,
                             float* partials, void* stream) {
     if (!partials) return USL_ERR_ARG;
+    DeviceGuard guard(partials);
     int rc = USL_OK;
     if (try_col(cfgs, scales, n_scales, false, partials, nullptr, nullptr, 0,
                 0, (cudaStream_t)stream, &rc))
@@ -384,6 +386,7 @@ extern "C" int usl_loss_reduce(const float* partials, const int* cta_starts,
     if (!partials || !cta_starts || !sums || n_scales < 1 ||
         n_scales > USL_MAX_SCALES)
         return USL_ERR_ARG;
+    DeviceGuard guard(partials);
     CtaStarts st;
     for (int i = 0; i <= n_scales; ++i) st.v[i] = cta_starts[i];
     reduce_partials_kernel<<<n_scales * NUM_ACC, 256, 0, (cudaStream_t)stream>>>(
@@ -396,6 +399,7 @@ extern "C" int usl_loss_combine(const double* sums, const float* coef,
                                 void* stream) {
     if (!sums || !coef || !out_disp || !out_err || n_scales < 1)
         return USL_ERR_ARG;
+    DeviceGuard guard(sums);
     combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, coef, n_scales,
                                                        out_disp, out_err);
     return check_launch();
@@ -462,6 +466,8 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
                              const UslLossScale* scales, int n_scales,
                              const float* gout_disp, const float* gout_err,
                              float* partials, int flags, void* stream) {
+    if (!cfgs || !scales || n_scales < 1) return USL_ERR_ARG;
+    DeviceGuard guard(scales[0].images);
     if (!col_ready(cfgs, scales, n_scales, true)) return USL_ERR_UNSUPPORTED;
     LossParams P[USL_MAX_SCALES];
     int rc = fill_all(cfgs, scales, n_scales, false, P);
@@ -487,6 +493,7 @@ extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
                             int stages, void* stream) {
     if (!(stages & (USL_BWD_STAGE_SCATTER | USL_BWD_STAGE_MAIN)))
         return USL_ERR_ARG;
+    DeviceGuard guard((scales && n_scales > 0) ? scales[0].images : nullptr);
     int rc = USL_OK;
     if (gout_disp && gout_err && col_ready(cfgs, scales, n_scales, true)) {
         LossParams P[USL_MAX_SCALES];

@@ -73,6 +73,7 @@ extern "C" int usl_pool3_fwd(const float* x, long long x_bs, long long x_cs,
                              int B, int C, int h, int w, float* out,
                              void* stream) {
     if (!x || !out || B <= 0 || C <= 0) return USL_ERR_ARG;
+    usl::DeviceGuard guard(x);
     if (h < 3 || w < 3) return USL_ERR_UNSUPPORTED;
     const long long total = (long long)B * C * (h - 2) * (w - 2);
     usl::pool3_fwd_kernel<<<usl::grid_for(total), 256, 0, (cudaStream_t)stream>>>(
@@ -83,6 +84,7 @@ extern "C" int usl_pool3_fwd(const float* x, long long x_bs, long long x_cs,
 extern "C" int usl_pool3_bwd(const float* grad_out, int B, int C, int h, int w,
                              float* grad_x, void* stream) {
     if (!grad_out || !grad_x || B <= 0 || C <= 0) return USL_ERR_ARG;
+    usl::DeviceGuard guard(grad_out);
     if (h < 3 || w < 3) return USL_ERR_UNSUPPORTED;
     const long long total = (long long)B * C * h * w;
     usl::pool3_bwd_kernel<<<usl::grid_for(total), 256, 0, (cudaStream_t)stream>>>(

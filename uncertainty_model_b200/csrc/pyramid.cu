@@ -87,6 +87,7 @@ extern "C" int usl_pyramid(const float* src, int B, int C, int H, int W,
         scales > USL_MAX_SCALES)
         return USL_ERR_ARG;
     if (scales == 1) return USL_OK;
+    DeviceGuard guard(src);
     PyramidParams p;
     p.src = src; p.src_bs = src_bs; p.src_cs = src_cs;
     p.B = B; p.C = C; p.H = H; p.W = W;

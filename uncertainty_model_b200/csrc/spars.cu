@@ -464,6 +464,7 @@ extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
         return USL_ERR_ARG;
     if (k < 1 || k > KMAX || H < k || W < k || steps > USL_MAX_STEPS)
         return USL_ERR_UNSUPPORTED;
+    DeviceGuard guard(oracle);
     if ((long long)rows * (H - k + 1) * (W - k + 1) >= (1ll << 31))
         return USL_ERR_UNSUPPORTED;
     const bool with_idx = order_out != nullptr;
@@ -549,6 +550,7 @@ extern "C" int usl_spars_finish(const double* row_norm_sum, int steps,
                                 long long total_rows, float* curve,
                                 void* stream) {
     if (!row_norm_sum || !curve || steps < 1 || total_rows < 1) return USL_ERR_ARG;
+    DeviceGuard guard(row_norm_sum);
     finish_kernel<<<(steps + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         row_norm_sum, steps, (double)total_rows, curve);
     return check_launch();
@@ -557,6 +559,7 @@ extern "C" int usl_spars_finish(const double* row_norm_sum, int steps,
 extern "C" int usl_spars_ause(const float* oracle_curve, const float* pred_curve,
                               int steps, float* out, void* stream) {
     if (!oracle_curve || !pred_curve || !out || steps < 1) return USL_ERR_ARG;
+    DeviceGuard guard(out);
     ause_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(oracle_curve, pred_curve,
                                                     steps, out);
     return check_launch();

@@ -27,6 +27,26 @@ inline int num_sms() {
     return cached;
 }
 
+// Every entry point launches on the device that owns its tensors: the guard
+// makes that device current for the call and restores the caller's afterwards
+// (the reference's DDP launcher moves everything `.to(cuda:i)` without ever
+// calling torch.cuda.set_device, parallel_main.py:152-160).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const void* p) {
+        if (!p) return;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return; }
+        if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return;
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) return;
+        if (cur != a.device && cudaSetDevice(a.device) == cudaSuccess) prev = cur;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // Side streams for launches that may run concurrently with what is on the
 // caller's stream: one small pool per host thread and device, created on first
 // use and never destroyed (immutable afterwards; nothing is shared between

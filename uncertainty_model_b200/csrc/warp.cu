@@ -83,6 +83,7 @@ extern "C" int usl_warp_fwd(const float* disp, long long disp_bs, float sign,
                             float* out, long long out_bs, long long out_cs,
                             void* stream) {
     if (!disp || !image || !out) return USL_ERR_ARG;
+    usl::DeviceGuard guard(image);
     usl::WarpParams p = {};
     p.disp = disp; p.disp_bs = disp_bs; p.sign = sign;
     p.image = image; p.img_bs = img_bs; p.img_cs = img_cs;
@@ -99,6 +100,7 @@ extern "C" int usl_warp_bwd_disp(const float* disp, long long disp_bs,
                                  float* grad_disp, long long gd_bs,
                                  void* stream) {
     if (!disp || !image || !grad_out || !grad_disp) return USL_ERR_ARG;
+    usl::DeviceGuard guard(image);
     usl::WarpParams p = {};
     p.disp = disp; p.disp_bs = disp_bs; p.sign = sign;
     p.image = image; p.img_bs = img_bs; p.img_cs = img_cs;
