@@ -416,7 +416,7 @@ def kernel_times(K, U, fn, sets, dev, reps):
         grads = []
         for i in range(4):
             bb, _, hh, ww = preds[i].shape
-            coefs = st.coefs(i, bb * fn.world_size * hh * ww)
+            coefs = st.coefs(i, bb * fn.grad_world_size * hh * ww)
             cfgs.append(K.make_config(st.terms(), st, coefs))
             pd = preds[i].detach()
             g = torch.empty_like(pd)

@@ -20,7 +20,10 @@
  *     for its duration and restores the caller's (the reference's DDP launcher
  *     never calls torch.cuda.set_device, parallel_main.py:152-160);
  *   - return value: USL_OK or a negative UslError; never throws, never exits.
- *   - re-entrant: no global mutable state.
+ *   - re-entrant.  State: tables that are written once and immutable
+ *     afterwards (tuning knobs read from the environment at first use, SM
+ *     counts) and, per host thread and device, a small pool of side streams
+ *     and events for the concurrent per-scale launches.
  */
 #ifndef USL_H_
 #define USL_H_
@@ -91,9 +94,12 @@ typedef struct UslLossConfig {
     float coef[USL_NUM_TERMS];
 } UslLossConfig;
 
+/* keep this call on the general strip kernels (tests: same result either way) */
+#define USL_SCALE_GENERAL_KERNELS 1
+
 typedef struct UslLossScale {
     int32_t B, h, w;
-    int32_t reserved;
+    int32_t flags;              /* USL_SCALE_* (0 = default) */
     const float* images;  int64_t img_bs, img_cs;    /* (B,6,h,w) L_rgb,R_rgb */
     const float* disp;    int64_t disp_bs, disp_cs;  /* (B,2,h,w) d_L,d_R     */
     const float* unc;     int64_t unc_bs, unc_cs;    /* (B,2,h,w) u_L,u_R     */

@@ -204,3 +204,20 @@ def step(stereo: Tensor, preds: Sequence[Tensor],
     dl, el = total_loss(pyr, preds, rec, config)
     (dl + el).backward()
     return dl.detach(), el.detach(), [p.grad for p in preds]
+
+
+def step_detailed(stereo: Tensor, preds: Sequence[Tensor],
+                  config: Optional[dict] = None) -> dict:
+    """`step` plus the intermediates a parity test needs to say WHERE the
+    gradient is one-sided (oracle/kinks.py): the pyramid, the reconstructions
+    and the per-scale error maps."""
+    preds = [p.detach().clone().requires_grad_(True) for p in preds]
+    pyr = pyramid(stereo, len(preds))
+    rec = recon_pyramid(preds, pyr)
+    dl, el, terms = total_loss(pyr, preds, rec, config, return_terms=True)
+    (dl + el).backward()
+    return dict(disp_loss=dl.detach(), error_loss=el.detach(),
+                grads=[p.grad for p in preds], pyramid=pyr,
+                preds=[p.detach() for p in preds],
+                recons=[r.detach() for r in rec],
+                errors=[e.detach() for e in terms['errors']])

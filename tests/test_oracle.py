@@ -192,3 +192,47 @@ def test_port_against_live_reference():
     assert float(el) == pytest.approx(float(rel), rel=1e-6)
     for a, b in zip(grads, pr):
         assert torch.allclose(a, b.grad, atol=1e-7)
+
+
+# ------------------------------------------------------------- kink masks --
+@pytest.mark.parametrize('name', sorted(LOSS_CASES))
+def test_kink_mask_accounts_for_fp32_vs_fp64_of_the_reference(name):
+    """oracle/kinks.py, the explicit mask of the parity metric (tests/parity.py):
+    the REAL reference's fp32 gradients (fixture) agree with its fp64 gradients
+    element by element outside the mask -- every element that differs by more
+    than rounding is one where the loss is one-sided."""
+    import parity
+    g = load(f'loss_{name}.npz')
+    cfg = LOSS_CASES[name]
+    stereo = torch.cat([torch.from_numpy(g['left']),
+                        torch.from_numpy(g['right'])], 1)
+    preds = [torch.from_numpy(g[f'pred{i}']) for i in range(4)]
+    ref = parity.oracle_reference(stereo, preds, cfg)
+    parity.check_grads([g[f'grad{i}_f32'] for i in range(4)],
+                       [g[f'grad{i}_f64'] for i in range(4)], ref['masks'],
+                       name, mask_max=ref['mask_max'])
+
+
+def test_kink_mask_margins_and_explicit_warp():
+    """The tap-by-tap warp behind the masks equals the oracle's grid_sample,
+    and the coordinate margin covers the fp32 evaluation with room to spare."""
+    import parity
+    from oracle import kinks as K
+    cfg = loss_config('l1')
+    left, right, preds = make_inputs(2, 128, 512, 0.3, 0)
+    stereo = torch.cat([left, right], 1)
+    p64 = preds[0].double()
+    im64 = stereo.double()
+    ew = K.explicit_warp(-p64[:, 0:1], im64[:, 3:6])
+    assert torch.allclose(ew['out'], P.warp_to_left(p64[:, 0:1], im64[:, 3:6]),
+                          atol=1e-14)
+    ix32 = K.explicit_warp(-preds[0][:, 0:1], stereo[:, 3:6])['ix']
+    worst = float((ix32.double() - ew['ix']).abs().max())
+    assert worst <= 0.5 * K.IX_EPS_PER_W * 512, worst
+    # the fp32 oracle passes the metric the CUDA path is held to
+    ref = parity.oracle_reference(stereo, preds, cfg)
+    _, _, g32 = P.step(stereo, preds, cfg)
+    stats = parity.check_grads(g32, ref['grads'], ref['masks'])
+    # ... and would not pass untrimmed: the masked elements carry the error
+    assert max(s['full'] for s in stats) > 10 * parity.GRAD_REL
+    assert max(s['masked'] for s in stats) < 1e-3

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, 'libusl.so')
 USL_NUM_TERMS = 6
 USL_MAX_SCALES = 8
 USL_ERR_UNSUPPORTED = -3
+USL_SCALE_GENERAL_KERNELS = 1
 
 TERM_REPROJ, TERM_CONS_D, TERM_SMOOTH_D = 1, 2, 4
 TERM_UNC, TERM_SMOOTH_U, TERM_CONS_U = 8, 16, 32
@@ -29,7 +30,7 @@ class UslLossConfig(C.Structure):
 class UslLossScale(C.Structure):
     _fields_ = [
         ('B', C.c_int32), ('h', C.c_int32), ('w', C.c_int32),
-        ('reserved', C.c_int32),
+        ('flags', C.c_int32),
         ('images', _f32p), ('img_bs', C.c_int64), ('img_cs', C.c_int64),
         ('disp', _f32p), ('disp_bs', C.c_int64), ('disp_cs', C.c_int64),
         ('unc', _f32p), ('unc_bs', C.c_int64), ('unc_cs', C.c_int64),

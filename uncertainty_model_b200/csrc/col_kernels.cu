@@ -13,17 +13,13 @@
 namespace usl {
 
 // ------------------------------------------------------------------ host ---
-static int env_int3(const char* name, int dflt) {
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    const int x = atoi(v);
-    return x > 0 ? x : dflt;
-}
+static int pos_or(int v, int dflt) { return v > 0 ? v : dflt; }
 
 bool col_eligible(const UslLossConfig* cfgs, const UslLossScale* scales, int n) {
-    if (getenv("USL_NO_COL")) return false;
+    if (knobs().no_col) return false;
     for (int i = 0; i < n; ++i) {
         const UslLossScale& s = scales[i];
+        if (s.flags & USL_SCALE_GENERAL_KERNELS) return false;
         const unsigned t = cfgs[i].terms;
         if (!(t & TERM_REPROJ) || s.recon_in || s.err_in) return false;
         if (!s.images || !s.disp) return false;
@@ -43,12 +39,12 @@ bool col_eligible(const UslLossConfig* cfgs, const UslLossScale* scales, int n) 
 static int col_plan_floor(ColPlan* M, bool grad, int floorR) {
     const int maxT = COL_MAX_THREADS;
     // widest two-view unit (in threads): wider rows get one unit per view
-    const int maxT2 = env_int3("USL_COL_MAXT2", COL_MAX_THREADS);
+    const int maxT2 = pos_or(knobs().col_maxt2, COL_MAX_THREADS);
     // Strip heights.  The CTAs of the largest scale are long and hold a whole
     // SM each (registers); the other scales run beside them only on the SMs
     // they leave free.  Measured best (profiles/, config 2): the largest scale
     // on ~2/3 of the SMs in ONE wave, 32-row strips below.
-    const int R0 = env_int3("USL_COL_R0", 0), R1 = env_int3("USL_COL_R", floorR);
+    const int R0 = pos_or(knobs().col_r0, 0), R1 = pos_or(knobs().col_r, floorR);
     long long rows = 0;
     for (int i = 0; i < M->n; ++i) {
         LossParams& p = M->P[i];
@@ -102,7 +98,7 @@ static int col_plan_floor(ColPlan* M, bool grad, int floorR) {
             ((((uintptr_t)p.img | (uintptr_t)p.disp | (uintptr_t)p.unc) & 15) == 0) &&
             (((p.img_bs | p.img_cs | p.d_bs | p.d_cs | p.u_bs | p.u_cs) & 3) == 0);
         M->mode[i] = tiles > 1 ? ck::MODE_TILED
-                               : (((nt & 31) || !al || getenv("USL_COL_NO_TMA"))
+                               : (((nt & 31) || !al || knobs().col_no_tma)
                                       ? ck::MODE_MASKED : ck::MODE_PLAIN);
         M->smem[i] = ck::c_floats(col_class_srow(cls), p.w, nv, R, grad) * sizeof(float);
         if (M->smem[i] > 220 * 1024) return USL_ERR_UNSUPPORTED;
@@ -137,8 +133,7 @@ extern template int col_launch_class<64>(const ColPlan*, int, bool, int, cudaStr
 int col_launch_scale(const ColPlan* M, int i, bool grad, int skip_if_unit,
                      cudaStream_t st) {
     // (profiling aid: USL_COL_ONLY = bit mask of the scales to launch)
-    static const int only = env_int3("USL_COL_ONLY", 0xff);
-    if (!((only >> i) & 1)) return USL_OK;
+    if (!((knobs().col_only >> i) & 1)) return USL_OK;
     switch (M->cls[i]) {
         case 512: return col_launch_class<512>(M, i, grad, skip_if_unit, st);
         case 256: return col_launch_class<256>(M, i, grad, skip_if_unit, st);
@@ -149,7 +144,7 @@ int col_launch_scale(const ColPlan* M, int i, bool grad, int skip_if_unit,
 }
 
 int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st) {
-    StreamPool* pool = (M->n > 1 && !getenv("USL_COL_SERIAL")) ? stream_pool() : nullptr;
+    StreamPool* pool = (M->n > 1 && !knobs().col_serial) ? stream_pool() : nullptr;
     if (!pool) {
         for (int i = 0; i < M->n; ++i) {
             const int rc = col_launch_scale(M, i, grad, skip_if_unit, st);
@@ -162,7 +157,7 @@ int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st) {
     // same moment (graph replay) its CTAs -- a whole SM each, the longest of
     // the step -- must be placed first, not behind the small scales' CTAs.
     if (cudaEventRecord(pool->fork, st) != cudaSuccess) return USL_ERR_CUDA;
-    const bool hi = !getenv("USL_COL_NO_PRIORITY");
+    const bool hi = !knobs().col_no_priority;
     int rc = USL_OK;
     if (hi) {
         if (cudaStreamWaitEvent(pool->first, pool->fork, 0) != cudaSuccess) return USL_ERR_CUDA;

@@ -182,16 +182,11 @@ __global__ void combine_kernel(const double* sums, const float* coef,
 }
 
 // ------------------------------------------------------------------ host ---
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    const int x = atoi(v);
-    return x > 0 ? x : dflt;
-}
+static int pos_or(int v, int dflt) { return v > 0 ? v : dflt; }
 
 static void choose_tiling(int h, int w, bool bwd, int* TW, int* R) {
-    int tw = env_int(bwd ? "USL_BWD_TW" : "USL_FWD_TW", bwd ? 128 : 256);
-    int r = env_int(bwd ? "USL_BWD_R" : "USL_FWD_R", 32);
+    int tw = pos_or(bwd ? knobs().bwd_tw : knobs().fwd_tw, bwd ? 128 : 256);
+    int r = pos_or(bwd ? knobs().bwd_r : knobs().fwd_r, 32);
     if (tw > w) tw = w;
     // even out the column tiles
     const int nx = (w + tw - 1) / tw;
@@ -276,6 +271,18 @@ static int plan(const UslLossConfig* cfgs, const UslLossScale* scales, int n,
 
 using namespace usl;
 
+// Any tensor of the call names the device it runs on (stand-alone terms pass
+// no images).
+static const void* any_tensor(const UslLossScale* s, int n) {
+    for (int i = 0; s && i < n; ++i) {
+        const void* c[] = {s[i].images, s[i].disp, s[i].unc, s[i].recon_in,
+                           s[i].err_in, s[i].grad_disp, s[i].grad_unc};
+        for (const void* p : c)
+            if (p) return p;
+    }
+    return nullptr;
+}
+
 static int fill_all(const UslLossConfig* cfgs, const UslLossScale* scales,
                     int n, bool bwd, LossParams* P) {
     if (n < 1 || n > USL_MAX_SCALES) return USL_ERR_ARG;
@@ -290,7 +297,7 @@ extern "C" int usl_loss_plan(const UslLossConfig* cfgs,
                              const UslLossScale* scales, int n_scales,
                              int mode, int* cta_starts) {
     if (!cfgs || !scales || !cta_starts) return USL_ERR_ARG;
-    DeviceGuard guard(n_scales > 0 ? scales[0].images : nullptr);
+    DeviceGuard guard(any_tensor(scales, n_scales));
     if (mode != USL_MODE_FWD && mode != USL_MODE_GRAD) return USL_ERR_ARG;
     if (col_eligible(cfgs, scales, n_scales)) {
         ColPlan M;
@@ -428,7 +435,7 @@ static int launch_scatter(const LossParams* P, int n_scales,
         c.accumulate = accumulate;
         c.terms = p.terms & (TERM_CONS_D | TERM_CONS_U);
         c.coef_dd = p.coef[ACC_CONS_D]; c.coef_ud = p.coef[ACC_CONS_U];
-        c.R = env_int("USL_CONS_R", 16);
+        c.R = pos_or(knobs().cons_r, 16);
         if (c.R > c.h) c.R = c.h;
         const int k = C.n++;
         C.P[k] = c;
@@ -438,12 +445,12 @@ static int launch_scatter(const LossParams* P, int n_scales,
         if (bytes > csmem) csmem = bytes;
     }
     *rc_out = USL_OK;
-    if (C.n > 0 && launch && !getenv("USL_SCATTER_V1")) {
+    if (C.n > 0 && launch && !knobs().scatter_v1) {
         const int rc2 = cons_scatter2_launch(&C, st);
         if (rc2 != USL_ERR_UNSUPPORTED) { *rc_out = rc2; return C.n; }
         // (rows too wide for the warp-per-row arena: the strip kernel below)
         for (int k = 0; k < C.n; ++k) {
-            C.P[k].R = env_int("USL_CONS_R", 16);
+            C.P[k].R = pos_or(knobs().cons_r, 16);
             if (C.P[k].R > C.P[k].h) C.P[k].R = C.P[k].h;
             C.strips[k] = (C.P[k].h + C.P[k].R - 1) / C.P[k].R;
             C.cta_start[k + 1] = C.cta_start[k] + C.strips[k] * C.P[k].B;
@@ -467,7 +474,7 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
                              const float* gout_disp, const float* gout_err,
                              float* partials, int flags, void* stream) {
     if (!cfgs || !scales || n_scales < 1) return USL_ERR_ARG;
-    DeviceGuard guard(scales[0].images);
+    DeviceGuard guard(any_tensor(scales, n_scales));
     if (!col_ready(cfgs, scales, n_scales, true)) return USL_ERR_UNSUPPORTED;
     LossParams P[USL_MAX_SCALES];
     int rc = fill_all(cfgs, scales, n_scales, false, P);
@@ -493,7 +500,7 @@ extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
                             int stages, void* stream) {
     if (!(stages & (USL_BWD_STAGE_SCATTER | USL_BWD_STAGE_MAIN)))
         return USL_ERR_ARG;
-    DeviceGuard guard((scales && n_scales > 0) ? scales[0].images : nullptr);
+    DeviceGuard guard(any_tensor(scales, n_scales));
     int rc = USL_OK;
     if (gout_disp && gout_err && col_ready(cfgs, scales, n_scales, true)) {
         LossParams P[USL_MAX_SCALES];

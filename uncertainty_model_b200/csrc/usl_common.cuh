@@ -3,6 +3,9 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "usl_math.cuh"
 #include "../../include/usl.h"
@@ -14,17 +17,68 @@ inline int check_launch() {
     return (e == cudaSuccess) ? USL_OK : USL_ERR_CUDA;
 }
 
+// SM count of the current device (cached per device; the cache is write-once
+// per slot, so concurrent first calls agree).
 inline int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) !=
-                cudaSuccess || n <= 0)
-            return 148;
-        cached = n;
-    }
-    return cached;
+    constexpr int MAX_DEV = 64;
+    static std::atomic<int> cached[MAX_DEV];
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 148;
+    n = cached[dev].load(std::memory_order_relaxed);
+    if (n > 0) return n;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) !=
+            cudaSuccess || n <= 0)
+        return 148;
+    cached[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
+
+// Tuning / profiling knobs, read from the environment ONCE (first use; C++11
+// guarantees the initialisation is thread safe) and immutable afterwards: the
+// launch paths never call getenv.  Unset = the built-in heuristics.
+struct Knobs {
+    int no_col;          // USL_NO_COL: keep every call on the general strip kernels
+    int col_maxt2;       // USL_COL_MAXT2: widest two-view unit, in threads
+    int col_r0, col_r;   // USL_COL_R0 / USL_COL_R: strip heights (scale 0 / others)
+    int col_no_tma;      // USL_COL_NO_TMA
+    int col_only;        // USL_COL_ONLY: bit mask of the scales to launch
+    int col_serial;      // USL_COL_SERIAL: all scales on the caller's stream
+    int col_no_priority; // USL_COL_NO_PRIORITY
+    int col_queue;       // USL_COL_QUEUE: persistent work-queue launch (0/1, -1 auto)
+    int fwd_tw, fwd_r, bwd_tw, bwd_r;   // USL_{FWD,BWD}_{TW,R}: general kernels
+    int cons_r;          // USL_CONS_R
+    int scatter_v1;      // USL_SCATTER_V1
+    int exp[8];          // USL_EXP0..7: experiment switches (tuning runs)
+};
+inline int knob_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoi(v);
+}
+inline const Knobs& knobs() {
+    static const Knobs k = [] {
+        Knobs x;
+        x.no_col = knob_int("USL_NO_COL", 0);
+        x.col_maxt2 = knob_int("USL_COL_MAXT2", 0);
+        x.col_r0 = knob_int("USL_COL_R0", 0);
+        x.col_r = knob_int("USL_COL_R", 0);
+        x.col_no_tma = knob_int("USL_COL_NO_TMA", 0);
+        x.col_only = knob_int("USL_COL_ONLY", 0xff);
+        x.col_serial = knob_int("USL_COL_SERIAL", 0);
+        x.col_no_priority = knob_int("USL_COL_NO_PRIORITY", 0);
+        x.col_queue = knob_int("USL_COL_QUEUE", -1);
+        x.fwd_tw = knob_int("USL_FWD_TW", 0);
+        x.fwd_r = knob_int("USL_FWD_R", 0);
+        x.bwd_tw = knob_int("USL_BWD_TW", 0);
+        x.bwd_r = knob_int("USL_BWD_R", 0);
+        x.cons_r = knob_int("USL_CONS_R", 0);
+        x.scatter_v1 = knob_int("USL_SCATTER_V1", 0);
+        const char* names[8] = {"USL_EXP0", "USL_EXP1", "USL_EXP2", "USL_EXP3",
+                                "USL_EXP4", "USL_EXP5", "USL_EXP6", "USL_EXP7"};
+        for (int i = 0; i < 8; ++i) x.exp[i] = knob_int(names[i], 0);
+        return x;
+    }();
+    return k;
 }
 
 // Every entry point launches on the device that owns its tensors: the guard

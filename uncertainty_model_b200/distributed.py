@@ -5,9 +5,21 @@ kernels on its own shard.  The only collective is one NCCL all-reduce of the
 raw per-term sums (fp64, scales x 6 values) per step -- issued between the
 fused forward launch and the 2-float combine kernel, on the same stream, with
 no host synchronisation -- so that every rank reports the loss of the GLOBAL
-batch and scales its local gradients by 1/(B_global*h*w).  With equal shards
-this is exactly what the reference's DDP run computes after gradient
-averaging (parallel_main.py:156-160 leaves the loss itself un-reduced).
+batch (the reference leaves the loss un-reduced, parallel_main.py:156-160:
+rank 0 logs its own shard's).
+
+Gradients come in two normalisations (`shard_loss(..., gradients=)`):
+
+  'ddp'     gradients of the LOCAL mean, 1/(B_local*h*w) -- what the
+            reference's launcher needs: it wraps the model in
+            DistributedDataParallel (parallel_main.py:158), which AVERAGES the
+            parameter gradients over ranks, and the average of the local-mean
+            gradients is the global-mean gradient.  Default.
+  'global'  gradients of the GLOBAL mean, 1/(B_global*h*w): every rank's
+            gradient w.r.t. its predictions is the matching slice of the
+            full-batch gradient.  For a gradient SUM all-reduce, or when the
+            prediction gradients are consumed directly -- NOT under torch DDP
+            (the parameter gradients would come out 1/world too small).
 
 Sparsification shards over frames the same way: all-reduce the per-step sums
 of normalised tail means and the row count.
@@ -28,14 +40,20 @@ def shard_bounds(total: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def shard_loss(loss_module, group: Optional['dist.ProcessGroup'] = None):
-    """Make a `TukraUncertaintyLoss` report global-batch losses.
+def shard_loss(loss_module, group: Optional['dist.ProcessGroup'] = None,
+               gradients: str = 'ddp'):
+    """Make a `TukraUncertaintyLoss` report global-batch losses; `gradients`
+    selects their normalisation (module docstring): 'ddp' | 'global'.
 
     Requires equal shard sizes on all ranks (as `DistributedSampler` gives)."""
+    if gradients not in ('ddp', 'global'):
+        raise ValueError("gradients must be 'ddp' or 'global'")
     if not dist.is_initialized():
         raise RuntimeError('torch.distributed is not initialised')
     loss_module.reduce_group = group if group is not None else dist.group.WORLD
     loss_module.world_size = dist.get_world_size(group)
+    loss_module.grad_world_size = \
+        loss_module.world_size if gradients == 'global' else 1
     return loss_module
 
 

@@ -135,9 +135,11 @@ def make_scale(images: Optional[Tensor], disp: Optional[Tensor],
                grad_recon_in: Optional[Tensor] = None,
                grad_disp: Optional[Tensor] = None,
                grad_unc: Optional[Tensor] = None,
-               grad_recon_out: Optional[Tensor] = None) -> UslLossScale:
+               grad_recon_out: Optional[Tensor] = None,
+               flags: int = 0) -> UslLossScale:
     s = UslLossScale()
     s.B, s.h, s.w = shape
+    s.flags = flags
     s.images = _ptr(images); s.img_bs, s.img_cs = _strides(images)
     s.disp = _ptr(disp); s.disp_bs, s.disp_cs = _strides(disp)
     s.unc = _ptr(unc); s.unc_bs, s.unc_cs = _strides(unc)
@@ -177,15 +179,28 @@ def plan_rows(cfg_arr, sc_arr, n: int, mode: int) -> Optional[List[int]]:
     return list(starts)
 
 
+class Reduce:
+    """How a sharded batch is put together: the raw term sums are all-reduced
+    over `group`; `combine_scale` turns the coefficients the kernels used (and
+    scaled the gradients with) into those of the reported loss -- 1 when the
+    kernels already normalise by the global batch, 1/world when they normalise
+    by the local shard (torch DDP averages parameter gradients itself)."""
+    __slots__ = ('group', 'combine_scale')
+
+    def __init__(self, group, combine_scale: float = 1.0) -> None:
+        self.group = group
+        self.combine_scale = float(combine_scale)
+
+
 def loss_forward(cfgs: Sequence[UslLossConfig],
                  scales: Sequence[UslLossScale], device,
-                 reduce_group=None, with_grad: bool = False,
+                 reduce: Optional[Reduce] = None, with_grad: bool = False,
                  arrays=None, starts: Optional[List[int]] = None
                  ) -> Tuple[Tensor, Tensor, Tensor]:
     """One fused launch over all scales.
 
     Returns (disp_loss, error_loss, sums): two 0-dim fp32 tensors and the
-    fp64[n_scales, 6] raw per-term sums (all-reduced over `reduce_group` when
+    fp64[n_scales, 6] raw per-term sums (all-reduced over `reduce.group` when
     the batch is sharded over ranks).
 
     with_grad: use the one-pass launch that also writes the gradients (for
@@ -203,7 +218,10 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
     sums = torch.empty(n, USL_NUM_TERMS, dtype=torch.float64, device=device)
     out_disp = torch.empty((), dtype=torch.float32, device=device)
     out_err = torch.empty((), dtype=torch.float32, device=device)
-    coef = coef_tensor(tuple(tuple(c.coef) for c in cfgs), device)
+    reduce_group = reduce.group if reduce is not None else None
+    cscale = reduce.combine_scale if reduce is not None else 1.0
+    coef = coef_tensor(tuple(tuple(k * cscale for k in c.coef) for c in cfgs),
+                       device)
     stream = _stream(partials)
     # sharded batch + gradients: the all-reduce of the sums only needs the fused
     # kernels, so it runs (NCCL stream) while the scatter kernel works
@@ -260,7 +278,7 @@ def loss_backward(cfgs: Sequence[UslLossConfig],
 
 
 def loss_regrad(arrays, n_scales: int, g_disp: Tensor, g_err: Tensor,
-                device) -> None:
+                device, skip_if_unit: bool = True) -> None:
     """Backward half of the one-pass scheme (`arrays`: the launch description
     of the forward): the gradients written by the
     forward are exact for unit upstream gradients; this launch recomputes them
@@ -270,7 +288,8 @@ def loss_regrad(arrays, n_scales: int, g_disp: Tensor, g_err: Tensor,
     cfg_arr, sc_arr = arrays
     check(lib().usl_loss_grad(cfg_arr, sc_arr, n_scales,
                               g_disp.data_ptr(), g_err.data_ptr(), None,
-                              GRAD_SKIP_IF_UNIT, stream), 'usl_loss_grad')
+                              GRAD_SKIP_IF_UNIT if skip_if_unit else 0,
+                              stream), 'usl_loss_grad')
 
 
 def pyramid(x: Tensor, scales: int) -> List[Tensor]:
@@ -435,6 +454,7 @@ class ScaleSpec:
     recon: int = -1         # given reconstruction (B,6,h,w)
     err: int = -1           # given error map (B,2,h,w)
     want_err: bool = False  # also return the (B,2,h,w) error map
+    flags: int = 0          # USL_SCALE_* (e.g. keep to the general kernels)
 
 
 def _pair(t: Tensor, ch: int) -> ChannelPair:
@@ -442,7 +462,7 @@ def _pair(t: Tensor, ch: int) -> ChannelPair:
 
 
 class FusedLoss(torch.autograd.Function):
-    """forward(settings, specs, group, *tensors) ->
+    """forward(settings, specs, reduce, *tensors) ->
            (disp_loss, error_loss, sums[n,6], error maps that were asked for...)
 
     Gradients are produced for the disparity / uncertainty tensors and for
@@ -493,12 +513,13 @@ class FusedLoss(torch.autograd.Function):
                 if sp.disp >= 0 and g[sp.disp] is not None else None,
                 grad_unc=_pair(g[sp.unc], sp.unc_ch)
                 if sp.unc >= 0 and g[sp.unc] is not None else None,
-                grad_recon_out=g[sp.recon] if sp.recon >= 0 else None))
+                grad_recon_out=g[sp.recon] if sp.recon >= 0 else None,
+                flags=sp.flags))
         return cfgs, scales
 
     @staticmethod
     def forward(ctx, settings: LossSettings, specs: Sequence[ScaleSpec],
-                group, *tensors: Tensor):
+                reduce: Optional[Reduce], *tensors: Tensor):
         for i, t in enumerate(tensors):
             require_cuda_f32(t, f'tensor {i}')
         tensors = tuple(planes(t) for t in tensors)
@@ -517,9 +538,10 @@ class FusedLoss(torch.autograd.Function):
             starts = plan_rows(arrays[0], arrays[1], n, MODE_GRAD)
             if starts is not None:
                 out_disp, out_err, sums = loss_forward(
-                    cfgs, scales, device, group, with_grad=True, arrays=arrays,
-                    starts=starts)
+                    cfgs, scales, device, reduce, with_grad=True,
+                    arrays=arrays, starts=starts)
                 ctx.onepass = grads
+                ctx.backward_calls = 0
                 # the same launch description serves the backward: the tensors
                 # it points to are kept alive by save_for_backward / `grads`;
                 # the error maps are outputs the caller may drop, so the
@@ -534,7 +556,7 @@ class FusedLoss(torch.autograd.Function):
             errs = []
         cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
                                         None, errs)
-        out_disp, out_err, sums = loss_forward(cfgs, scales, device, group)
+        out_disp, out_err, sums = loss_forward(cfgs, scales, device, reduce)
         ctx.save_for_backward(*tensors)
         ctx.mark_non_differentiable(sums, *errs)
         ctx.set_materialize_grads(False)
@@ -551,13 +573,28 @@ class FusedLoss(torch.autograd.Function):
             g_err = g_err.contiguous()
         needs = ctx.needs_input_grad[3:]
         if ctx.onepass is not None:
-            grads = ctx.onepass
             zero = None
             if g_disp is None or g_err is None:
                 zero = torch.zeros((), dtype=torch.float32, device=device)
-            loss_regrad(ctx.arrays, len(specs),
-                        zero if g_disp is None else g_disp,
-                        zero if g_err is None else g_err, device)
+            gd = zero if g_disp is None else g_disp
+            ge = zero if g_err is None else g_err
+            ctx.backward_calls += 1
+            if ctx.backward_calls == 1:
+                # the buffers hold the gradients for unit upstream gradients
+                # (written by the forward): redone in place only if (gd, ge)
+                # differ from (1, 1) -- decided on the device
+                grads = ctx.onepass
+                loss_regrad(ctx.arrays, len(specs), gd, ge, device, True)
+            else:
+                # backward(retain_graph=True) again: the first call's buffers
+                # were handed to autograd (and may hold non-unit gradients
+                # now), so this call computes into fresh ones, unconditionally
+                grads = FusedLoss._grad_buffers(specs, tensors)
+                cfgs, scales = FusedLoss._build(settings, specs, tensors,
+                                                device, grads)
+                arrays = (_array(UslLossConfig, cfgs),
+                          _array(UslLossScale, scales))
+                loss_regrad(arrays, len(specs), gd, ge, device, False)
             return (None, None, None) + tuple(
                 g if need else None for g, need in zip(grads, needs))
         grads = FusedLoss._grad_buffers(specs, tensors)

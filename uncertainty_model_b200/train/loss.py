@@ -218,9 +218,10 @@ class TukraUncertaintyLoss(nn.Module):
     untouched result of `utils.reconstruct_pyramid(predictions,
     image_pyramid)`; any other reconstruction pyramid is honoured as given.
 
-    Set `reduce_group` (see uncertainty_model_b200.distributed) to make the
-    returned losses -- and the gradient scaling -- those of the global batch
-    when the batch is sharded over ranks.
+    `uncertainty_model_b200.distributed.shard_loss` makes the returned losses
+    those of the global batch when the batch is sharded over ranks, with the
+    gradients either of the local mean (torch DDP averages them) or of the
+    global mean.
     """
 
     def __init__(self, wssim_weight: float = 1.0,
@@ -250,9 +251,12 @@ class TukraUncertaintyLoss(nn.Module):
         self.perceptual_weight = perceptual_weight
         self.predictive_error_weight = predictive_error_weight
 
+        # batch sharded over ranks (uncertainty_model_b200.distributed):
         self.reduce_group = None     # torch.distributed group, or None
-        self.world_size = 1
+        self.world_size = 1          # ranks the reported losses are means over
+        self.grad_world_size = 1     # ... the gradients are normalised by
         self.last_term_sums = None   # fp64 [scales, 6] raw sums (debugging)
+        self.kernel_flags = 0        # USL_SCALE_* of include/usl.h (tests)
 
     def _settings(self) -> LossSettings:
         pe = self.predictive_error
@@ -292,12 +296,13 @@ class TukraUncertaintyLoss(nn.Module):
         specs: List[ScaleSpec] = []
         for i in range(n_scales):
             b, _, h, w = preds[i].shape
-            coefs = st.coefs(i, b * self.world_size * h * w)
+            coefs = st.coefs(i, b * self.grad_world_size * h * w)
             if pooling:
                 coefs[3] = coefs[4] = coefs[5] = 0.0
             sp = ScaleSpec(terms=disp_terms if pooling
                            else disp_terms | err_terms,
-                           coefs=tuple(coefs), want_err=pooling)
+                           coefs=tuple(coefs), want_err=pooling,
+                           flags=self.kernel_flags)
             sp.images = len(tensors); tensors.append(images[i])
             sp.disp = sp.unc = len(tensors); tensors.append(preds[i])
             sp.disp_ch, sp.unc_ch = 0, 2
@@ -305,7 +310,11 @@ class TukraUncertaintyLoss(nn.Module):
                 sp.recon = len(tensors); tensors.append(recons[i])
             specs.append(sp)
 
-        out = FusedLoss.apply(st, specs, self.reduce_group, *tensors)
+        reduce = None
+        if self.reduce_group is not None:
+            reduce = K.Reduce(self.reduce_group,
+                              self.grad_world_size / self.world_size)
+        out = FusedLoss.apply(st, specs, reduce, *tensors)
         disp_loss, error_loss, sums = out[0], out[1], out[2]
         self.last_term_sums = sums
 
@@ -319,7 +328,7 @@ class TukraUncertaintyLoss(nn.Module):
                 pi = K.Pool3.apply(images[i])
                 pe = K.Pool3.apply(errs[i])
                 b, _, h, w = pp.shape
-                coefs = st.coefs(i, b * self.world_size * h * w)
+                coefs = st.coefs(i, b * self.grad_world_size * h * w)
                 coefs[0] = coefs[1] = coefs[2] = 0.0
                 sp = ScaleSpec(terms=err_terms, coefs=tuple(coefs))
                 sp.images = len(p_tensors); p_tensors.append(pi)
@@ -327,7 +336,7 @@ class TukraUncertaintyLoss(nn.Module):
                 sp.disp_ch, sp.unc_ch = 0, 2
                 sp.err = len(p_tensors); p_tensors.append(pe)
                 p_specs.append(sp)
-            error_loss = FusedLoss.apply(st, p_specs, self.reduce_group,
+            error_loss = FusedLoss.apply(st, p_specs, reduce,
                                          *p_tensors)[1]
             self.wssim._last_error = errs[-1]
         else:
