@@ -423,9 +423,12 @@ def kernel_times(K, U, fn, sets, dev, reps):
             grads.append(g)
             fsc.append(K.make_scale(pyr[i], pd[:, 0:2], pd[:, 2:4],
                                     shape=(bb, hh, ww)))
+            ws = torch.empty(bb * 2 * hh * ww * 4, dtype=torch.float32,
+                             device=dev)
+            grads.append(ws)
             bsc.append(K.make_scale(pyr[i], pd[:, 0:2], pd[:, 2:4],
                                     shape=(bb, hh, ww), grad_disp=g[:, 0:2],
-                                    grad_unc=g[:, 2:4]))
+                                    grad_unc=g[:, 2:4], scatter_ws=ws))
         prepared.append((stereo, pyr, cfgs, fsc, bsc, grads))
     one = torch.ones((), device=dev)
 
@@ -473,6 +476,19 @@ def kernel_times(K, U, fn, sets, dev, reps):
         prepared[i % nsets][2], prepared[i % nsets][4], one, one, dev, 1))
     out['loss_fused_main'] = t(lambda i: K.loss_backward(
         prepared[i % nsets][2], prepared[i % nsets][4], one, one, dev, 2))
+    # the two halves of the one-pass launch sequence, each alone: the fused
+    # kernels (they also leave the scatter inputs behind), then the scatter
+    def half(i, flag):
+        cfgs, _, bsc = prepared[i % nsets][2], None, prepared[i % nsets][4]
+        arr = (K._array(K.UslLossConfig, cfgs), K._array(K.UslLossScale, bsc))
+        K.check(K.lib().usl_loss_grad(arr[0], arr[1], 4, None, None, None, flag,
+                                      torch.cuda.current_stream().cuda_stream),
+                'usl_loss_grad')
+    try:
+        out['onepass_fused'] = t(lambda i: half(i, K.GRAD_NO_SCATTER))
+        out['onepass_scatter'] = t(lambda i: half(i, K.GRAD_ONLY_SCATTER))
+    except Exception:
+        out['onepass_fused'] = out['onepass_scatter'] = None
     # the training step's path: sums + gradients in one pass (scatter kernel,
     # marching kernel in GRAD mode, reduce, combine)
     try:

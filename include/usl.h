@@ -114,6 +114,13 @@ typedef struct UslLossScale {
     float* grad_disp;     int64_t gd_bs, gd_cs;      /* (B,2,h,w) [backward]  */
     float* grad_unc;      int64_t gu_bs, gu_cs;      /* (B,2,h,w) [backward]  */
     float* grad_recon_out;       /* contiguous (B,6,h,w) [backward, recon_in] */
+    float* scatter_ws;           /* optional workspace of usl_loss_grad /
+                              usl_loss_bwd, 32*B*h*w bytes, 16-byte aligned:
+                              the fused kernels leave {sampling column, signed
+                              coefficient} of both consistency terms per pixel
+                              and the transposed warp runs on the lane-per-row
+                              kernel fed from it (otherwise on the warp-per-row
+                              kernel, which recomputes the warp) */
 } UslLossScale;
 
 /* All pyramid scales of a step are processed by ONE launch: `cfgs` and

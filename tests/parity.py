@@ -10,9 +10,10 @@ by the size of the error.  Per channel of every scale:
   * every element outside the mask: relative L2 error <= GRAD_REL, and no
     single element off by more than ELEM_REL of the largest gradient value;
   * the masked elements are counted (fraction <= MASK_MAX: the margins are
-    ~1e-7 * width wide on both sides of an integer, so ~2e-4 of the pixels per
-    warp at w = 512 plus the sign kinks) and must still be finite and bounded
-    by the size of a one-sided jump;
+    2.5e-7 * width wide on both sides of an integer -- 2.6e-4 of the pixels at
+    w = 512, twice that at 1024 -- plus the sign kinks and the four taps each
+    of those scatters to: ~1e-3 .. 2e-3 in all) and must still be finite and
+    bounded by the size of a one-sided jump;
   * the untrimmed relative L2 error is reported (`stats`), never asserted: k
     legitimately one-sided elements out of n put ~sqrt(k/n) on it.
 """
@@ -24,7 +25,7 @@ import torch
 
 GRAD_REL = 1e-4
 ELEM_REL = 5e-4
-MASK_MAX = 2.5e-3
+MASK_MAX = 5e-3
 
 
 def oracle_reference(stereo, preds, cfg):

@@ -228,11 +228,11 @@ def test_kink_mask_margins_and_explicit_warp():
                           atol=1e-14)
     ix32 = K.explicit_warp(-preds[0][:, 0:1], stereo[:, 3:6])['ix']
     worst = float((ix32.double() - ew['ix']).abs().max())
-    assert worst <= 0.5 * K.IX_EPS_PER_W * 512, worst
+    assert worst <= 0.2 * K.IX_EPS_PER_W * 512, worst
     # the fp32 oracle passes the metric the CUDA path is held to
     ref = parity.oracle_reference(stereo, preds, cfg)
     _, _, g32 = P.step(stereo, preds, cfg)
     stats = parity.check_grads(g32, ref['grads'], ref['masks'])
     # ... and would not pass untrimmed: the masked elements carry the error
     assert max(s['full'] for s in stats) > 10 * parity.GRAD_REL
-    assert max(s['masked'] for s in stats) < 1e-3
+    assert max(s['masked'] for s in stats) < 2e-3

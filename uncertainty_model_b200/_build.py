@@ -15,7 +15,8 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libusl.so')
 SOURCES = ['pyramid.cu', 'warp.cu', 'misc.cu', 'loss_kernels.cu',
            'col_kernels.cu', 'col_inst_512.cu', 'col_inst_256.cu',
-           'col_inst_128.cu', 'col_inst_64.cu', 'cons_kernels.cu', 'spars.cu']
+           'col_inst_128.cu', 'col_inst_64.cu', 'cons_kernels.cu', 'cons_rows.cu',
+           'spars.cu']
 HEADERS = ['usl_math.cuh', 'usl_common.cuh', 'loss_core.cuh', 'cons_core.cuh',
            'col_core.cuh',
            'col_launch.cuh', 'col_kernel_impl.cuh', 'cons_launch.cuh',

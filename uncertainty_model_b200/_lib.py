@@ -41,6 +41,7 @@ class UslLossScale(C.Structure):
         ('grad_disp', _f32p), ('gd_bs', C.c_int64), ('gd_cs', C.c_int64),
         ('grad_unc', _f32p), ('gu_bs', C.c_int64), ('gu_cs', C.c_int64),
         ('grad_recon_out', _f32p),
+        ('scatter_ws', _f32p),
     ]
 
 

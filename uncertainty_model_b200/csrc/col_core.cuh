@@ -80,6 +80,9 @@ USL_HD F4 ld_f4(const F4* p) {
 USL_HD void st_f4(F4* p, float a, float b, float c, float d) {
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
+USL_HD void st_f2(float* p, float a, float b) {
+    *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
 #else
 USL_HD unsigned f2u(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 USL_HD float u2f(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
@@ -90,6 +93,7 @@ USL_HD F4 ld_f4(const F4* p) { return *p; }
 USL_HD void st_f4(F4* p, float a, float b, float c, float d) {
     p->x = a; p->y = b; p->z = c; p->w = d;
 }
+USL_HD void st_f2(float* p, float a, float b) { p[0] = a; p[1] = b; }
 #endif
 
 // s * sgn(v)   (torch: d|v|/dv = sign(v), 0 at 0): sign-bit transfer + zero test
@@ -279,6 +283,7 @@ struct CState {
     unsigned o_oi, o_od;        // ... of (b, opposite view, row 0, c): img, disp
     unsigned o_gd, o_gu;        // element offsets of the gradient outputs: (b, own view,
                                 // next row to be finalised, c)
+    unsigned o_sc;              // element offset of (b, own view, row 0, c) in P.scat
     int v, vi, c, lc;
     bool active, win_ok, has1;
 };
@@ -331,6 +336,7 @@ USL_HD void c_thread_init(const LossParams& P, const CGeo& G, const CRings& S,
                         (long long)G.ya * w + T.c);
     T.o_gu = (unsigned)((long long)G.b * P.gu_bs + (long long)T.v * P.gu_cs +
                         (long long)G.ya * w + T.c);
+    T.o_sc = (unsigned)(((long long)G.b * 2 + T.v) * ((long long)P.h * w) + T.c);
     T.txw = 0.f; T.axw = 0.f; T.ax0 = T.ax1 = 0;
     if (!T.active) return;
     const TapAC ax = ac_taps(T.c, G.sW, w - 2);
@@ -646,8 +652,8 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
 
     // ---- reconstruction of the row: two taps of V at the shifted column ----
     float wd, dwd = 0.f, dI[3];
+    const float ix = c_warp_coord(T.xbase, sign * T.d, hw);
     {
-        const float ix = c_warp_coord(T.xbase, sign * T.d, hw);
         const float f = floorf(ix);
         const float w1 = ix - f, w0 = (f + 1.0f) - ix;
         const int xi = (int)fminf(fmaxf(f, -2.0f), fw);
@@ -693,25 +699,36 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
             gdr = (-sign * kl1) * gl1;
         }
         // ---- consistency terms ----
+        // The transposed warp of both terms runs in cons_rows_kernel, lane per
+        // row; what it cannot recompute cheaply is the sign of (a - warp(b)), so
+        // the signed coefficients of the pixel are left behind, together with
+        // the two sampling columns (one 16-byte element per pixel: its rows then
+        // arrive there as bulk copies).
+        float s_dd = 0.f, s_ud = 0.f, ixu = 0.f;
         if (terms & TERM_CONS_D) {
             const float f = T.d - wd;
             T.acc[ACC_CONS_D] += own * fabsf(f);
-            if (GRAD)
-                gdr += sgn_mul(f, G.gd_up * P.coef[ACC_CONS_D]) *
-                       (1.0f - sign * dwd);
+            if (GRAD) {
+                s_dd = sgn_mul(f, G.gd_up * P.coef[ACC_CONS_D]);
+                gdr += s_dd * (1.0f - sign * dwd);
+            }
         }
         if (terms & TERM_CONS_U) {
-            const float ix = c_warp_coord(T.xbase, sign * T.u, hw);
-            const float f = floorf(ix);
-            const float w1 = ix - f, w0 = (f + 1.0f) - ix;
+            ixu = c_warp_coord(T.xbase, sign * T.u, hw);
+            const float f = floorf(ixu);
+            const float w1 = ixu - f, w0 = (f + 1.0f) - ixu;
             const int xi = (int)fminf(fmaxf(f, -2.0f), fw);
             const float g0 = T.vrow0[xi].w, g1 = T.vrow0[xi + 1].w;
             const float e = T.u - (w0 * g0 + w1 * g1);
             T.acc[ACC_CONS_U] += own * fabsf(e);
-            if (GRAD)
-                gur = sgn_mul(e, G.ge_up * P.coef[ACC_CONS_U]) *
-                      (1.0f - (sign * fw) * (g1 - g0));
+            if (GRAD) {
+                s_ud = sgn_mul(e, G.ge_up * P.coef[ACC_CONS_U]);
+                gur = s_ud * (1.0f - (sign * fw) * (g1 - g0));
+            }
         }
+        if (GRAD && P.scat && (!MASKED || own != 0.f))
+            st_f4(reinterpret_cast<F4*>(P.scat) + (T.o_sc + (unsigned)(r * P.w)),
+                  ix, ixu, s_dd, s_ud);
         if (GRAD) { T.gd[0] = gdr; T.gu[0] = gur; }
     }
 

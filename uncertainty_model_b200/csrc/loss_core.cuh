@@ -88,6 +88,11 @@ struct LossParams {
     float* grad_unc;  long long gu_bs, gu_cs;   // 2 planes
     float* grad_recon_out;       // (B,6,h,w) contiguous when recon is given
     int grad_disp_accumulate;    // add to what the scatter kernel stored
+    // input of the lane-per-row transposed warp of the consistency terms
+    // (column kernels -> cons_rows_kernel): [b][view][h*w] elements
+    // {sampling column of term dd, of term ud, coefficient * sign(a - warp(b))
+    // of term dd, of term ud}, or NULL
+    float* scat;
     // ---- configuration
     unsigned terms;
     int loss_type;

@@ -224,6 +224,7 @@ static int fill_params(const UslLossConfig* cfg, const UslLossScale* s,
     p.grad_disp = s->grad_disp; p.gd_bs = s->gd_bs; p.gd_cs = s->gd_cs;
     p.grad_unc = s->grad_unc; p.gu_bs = s->gu_bs; p.gu_cs = s->gu_cs;
     p.grad_recon_out = s->grad_recon_out;
+    p.scat = s->scatter_ws;
     p.terms = t; p.loss_type = cfg->loss_type;
     p.recon_given = s->recon_in != nullptr;
     p.err_given = s->err_in != nullptr;
@@ -417,10 +418,12 @@ extern "C" int usl_loss_combine(const double* sums, const float* coef,
 static int launch_scatter(const LossParams* P, int n_scales,
                           const float* gout_disp, const float* gout_err,
                           float gout_default, int skip_if_unit, bool launch,
-                          cudaStream_t st, int* rc_out, int accumulate = 0) {
+                          cudaStream_t st, int* rc_out, int accumulate = 0,
+                          bool scat_filled = false) {
     MultiCons C;
     C.n = 0; C.cta_start[0] = 0; C.skip_if_unit = skip_if_unit;
     size_t csmem = 0;
+    bool use_scat = scat_filled && !knobs().exp[0];
     for (int i = 0; i < n_scales; ++i) {
         const LossParams& p = P[i];
         if (!(p.terms & (TERM_CONS_D | TERM_CONS_U))) continue;
@@ -435,6 +438,8 @@ static int launch_scatter(const LossParams* P, int n_scales,
         c.accumulate = accumulate;
         c.terms = p.terms & (TERM_CONS_D | TERM_CONS_U);
         c.coef_dd = p.coef[ACC_CONS_D]; c.coef_ud = p.coef[ACC_CONS_U];
+        c.scat = p.scat;
+        use_scat = use_scat && p.scat != nullptr;
         c.R = pos_or(knobs().cons_r, 16);
         if (c.R > c.h) c.R = c.h;
         const int k = C.n++;
@@ -445,6 +450,11 @@ static int launch_scatter(const LossParams* P, int n_scales,
         if (bytes > csmem) csmem = bytes;
     }
     *rc_out = USL_OK;
+    if (C.n > 0 && launch && use_scat) {
+        // (the column kernels of this call left the per-pixel taps behind)
+        const int rc3 = cons_rows_launch(&C, st);
+        if (rc3 != USL_ERR_UNSUPPORTED) { *rc_out = rc3; return C.n; }
+    }
     if (C.n > 0 && launch && !knobs().scatter_v1) {
         const int rc2 = cons_scatter2_launch(&C, st);
         if (rc2 != USL_ERR_UNSUPPORTED) { *rc_out = rc2; return C.n; }
@@ -490,7 +500,7 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
     }
     if (!(flags & USL_GRAD_NO_SCATTER))
         launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
-                       (cudaStream_t)stream, &rc, 1);
+                       (cudaStream_t)stream, &rc, 1, true);
     return rc;
 }
 
@@ -516,7 +526,8 @@ extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,
         launch_scatter(P, n_scales, gout_disp, gout_err, 0.0f, 0,
                        (stages & USL_BWD_STAGE_SCATTER) != 0,
                        (cudaStream_t)stream, &rc,
-                       (stages & USL_BWD_STAGE_MAIN) ? 1 : 0);
+                       (stages & USL_BWD_STAGE_MAIN) ? 1 : 0,
+                       (stages & USL_BWD_STAGE_MAIN) != 0);
         return rc;
     }
     // (a NULL upstream gradient means "this output takes no part": the general

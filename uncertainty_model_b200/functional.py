@@ -136,6 +136,7 @@ def make_scale(images: Optional[Tensor], disp: Optional[Tensor],
                grad_disp: Optional[Tensor] = None,
                grad_unc: Optional[Tensor] = None,
                grad_recon_out: Optional[Tensor] = None,
+               scatter_ws: Optional[Tensor] = None,
                flags: int = 0) -> UslLossScale:
     s = UslLossScale()
     s.B, s.h, s.w = shape
@@ -151,6 +152,7 @@ def make_scale(images: Optional[Tensor], disp: Optional[Tensor],
     s.grad_disp = _ptr(grad_disp); s.gd_bs, s.gd_cs = _strides(grad_disp)
     s.grad_unc = _ptr(grad_unc); s.gu_bs, s.gu_cs = _strides(grad_unc)
     s.grad_recon_out = _ptr(grad_recon_out)
+    s.scatter_ws = _ptr(scatter_ws)
     return s
 
 
@@ -490,10 +492,21 @@ class FusedLoss(torch.autograd.Function):
         return grads
 
     @staticmethod
-    def _build(settings, specs, tensors, device, grads=None, errs=None):
+    def _build(settings, specs, tensors, device, grads=None, errs=None,
+               keep=None):
+        """`keep`: list that receives the workspaces the launch description
+        points to (they must outlive it)."""
         cfgs, scales = [], []
         for sp in specs:
             b, h, w = _spec_shape(sp, tensors)
+            ws = None
+            if grads is not None and keep is not None and \
+                    sp.terms & (TERM_CONS_D | TERM_CONS_U):
+                # {d, u, signed coefficients of the two consistency terms} per pixel
+                # for the transposed warp (include/usl.h: scatter_ws)
+                ws = torch.empty(b * 2 * h * w * 4, dtype=torch.float32,
+                                 device=device)
+                keep.append(ws)
             err_out = None
             if errs is not None and sp.want_err:
                 err_out = torch.empty(b, 2, h, w, dtype=torch.float32,
@@ -514,7 +527,7 @@ class FusedLoss(torch.autograd.Function):
                 grad_unc=_pair(g[sp.unc], sp.unc_ch)
                 if sp.unc >= 0 and g[sp.unc] is not None else None,
                 grad_recon_out=g[sp.recon] if sp.recon >= 0 else None,
-                flags=sp.flags))
+                scatter_ws=ws, flags=sp.flags))
         return cfgs, scales
 
     @staticmethod
@@ -531,8 +544,9 @@ class FusedLoss(torch.autograd.Function):
             # one pass: the sums and (for unit upstream gradients) the
             # gradients together -- see usl_loss_grad in include/usl.h
             grads = FusedLoss._grad_buffers(specs, tensors)
+            keep: List[Tensor] = []
             cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
-                                            grads, errs)
+                                            grads, errs, keep)
             n = len(scales)
             arrays = (_array(UslLossConfig, cfgs), _array(UslLossScale, scales))
             starts = plan_rows(arrays[0], arrays[1], n, MODE_GRAD)
@@ -541,6 +555,7 @@ class FusedLoss(torch.autograd.Function):
                     cfgs, scales, device, reduce, with_grad=True,
                     arrays=arrays, starts=starts)
                 ctx.onepass = grads
+                ctx.workspaces = keep
                 ctx.backward_calls = 0
                 # the same launch description serves the backward: the tensors
                 # it points to are kept alive by save_for_backward / `grads`;
@@ -590,16 +605,18 @@ class FusedLoss(torch.autograd.Function):
                 # were handed to autograd (and may hold non-unit gradients
                 # now), so this call computes into fresh ones, unconditionally
                 grads = FusedLoss._grad_buffers(specs, tensors)
+                keep = []
                 cfgs, scales = FusedLoss._build(settings, specs, tensors,
-                                                device, grads)
+                                                device, grads, keep=keep)
                 arrays = (_array(UslLossConfig, cfgs),
                           _array(UslLossScale, scales))
                 loss_regrad(arrays, len(specs), gd, ge, device, False)
             return (None, None, None) + tuple(
                 g if need else None for g, need in zip(grads, needs))
         grads = FusedLoss._grad_buffers(specs, tensors)
+        keep = []
         cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
-                                        grads)
+                                        grads, keep=keep)
         loss_backward(cfgs, scales, g_disp, g_err, device)
         return (None, None, None) + tuple(
             g if need else None for g, need in zip(grads, needs))
