@@ -116,8 +116,8 @@ typedef struct UslLossScale {
     float* grad_recon_out;       /* contiguous (B,6,h,w) [backward, recon_in] */
     float* scatter_ws;           /* optional workspace of usl_loss_grad /
                               usl_loss_bwd, 32*B*h*w bytes, 16-byte aligned:
-                              the fused kernels leave {sampling column, signed
-                              coefficient} of both consistency terms per pixel
+                              the fused kernels leave {d, u, signed coefficient
+                              of either consistency term} of every pixel there
                               and the transposed warp runs on the lane-per-row
                               kernel fed from it (otherwise on the warp-per-row
                               kernel, which recomputes the warp) */

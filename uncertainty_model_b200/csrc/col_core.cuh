@@ -164,12 +164,13 @@ constexpr int NHIST_GRAD = 11;  // dI[3], y*dI[3], x*dI[3], l1, u
 constexpr int NHIST_FWD = 2;    // l1, u
 constexpr int NSLOT = 4;        // input ring depth (rows r, r+1, r+2 | r+3 in flight)
 constexpr int NPL = 5;          // planes per ring slot: x[3], d, u
+constexpr int NPO = 4;          // ... of the opposite view's ring: x[3], d
 enum {
     ROW_Y = 0,      // [3]  recon of the current row        (right neighbours read)
     ROW_DS = 3,     // [4]  ring of channel-summed dssim rows
     ROW_IN = 7,     // [NSLOT][NPL] own view(s): image, disparity, uncertainty rows
-    ROW_OPP = 27,   // [NSLOT][NPL] opposite view (one-view units): image, disparity
-    ROW_HS = 47,    // [3][NH] thread-private history of the rows in flight
+    ROW_OPP = 27,   // [NSLOT][NPO] opposite view (one-view units): image, disparity
+    ROW_HS = 43,    // [3][NH] thread-private history of the rows in flight
 };
 USL_HD constexpr int row_gx(bool grad) {     // [9] G(q) of the current window row
     return ROW_HS + 3 * (grad ? NHIST_GRAD : NHIST_FWD);
@@ -227,6 +228,7 @@ struct CRings {
     uint32_t mbar_a;      // shared-window address of mbar[0]
     const float** isrc;   // [MAX_ISSUE] row 0 of every plane the ring holds
     int* idst;            // [MAX_ISSUE] float offset of its row inside a slot
+    int* istr;            // [MAX_ISSUE] floats from one slot to the next
 };
 constexpr int MAX_ISSUE = 10;
 
@@ -241,7 +243,7 @@ USL_HD size_t c_floats(int srow, int w, int nv, int R, bool grad) {
     size_t n = (size_t)n_rows(grad) * srow;
     n += (size_t)nv * (w + 2 * VPAD) * 4;
     n += (size_t)(R + 8) * 16;
-    n += 8 + 2 * MAX_ISSUE + 12;
+    n += 8 + 2 * MAX_ISSUE + 12 + 12;
     return (n + 3) & ~(size_t)3;
 }
 
@@ -256,6 +258,7 @@ USL_HD CRings c_carve(float* base, int srow, int w, int nv, int R, bool grad) {
     S.mbar_a = smem_u32(S.mbar);
     S.isrc = reinterpret_cast<const float**>(base); base += 2 * MAX_ISSUE;
     S.idst = reinterpret_cast<int*>(base); base += 12;
+    S.istr = reinterpret_cast<int*>(base); base += 12;
     S.rows = base;
     return S;
 }
@@ -408,8 +411,10 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
             v.w1 = ok1 ? ty.w1 : 0.0f;
             const int i0 = ok0 ? ty.i0 : ty.i0 + 1;
             const int i1 = ok1 ? ty.i0 + 1 : ty.i0;
-            v.o0 = c_ring_slot(G, i0) * NPL * SROW;
-            v.o1 = c_ring_slot(G, i1) * NPL * SROW;
+            // (the opposite view: the other segment of the own ring, or its own ring)
+            const int per_slot = (G.nv == 2 ? NPL : NPO) * SROW;
+            v.o0 = c_ring_slot(G, i0) * per_slot;
+            v.o1 = c_ring_slot(G, i1) * per_slot;
             ww.wait_v0 = c_wait_word(S, c_ring_slot(G, i0), c_ring_parity(G, i0));
             ww.wait_v1 = c_wait_word(S, c_ring_slot(G, i1), c_ring_parity(G, i1));
         }
@@ -447,12 +452,15 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
             const int dst = ROW_IN * SROW + vi * seg + SEG_PAD;
             for (int k = 0; k < 3; ++k) {
                 S.isrc[n] = plane(P.img, P.img_bs, P.img_cs, G.b, v * 3 + k);
+                S.istr[n] = NPL * SROW;
                 S.idst[n++] = dst + k * SROW;
             }
             S.isrc[n] = plane(P.disp, P.d_bs, P.d_cs, G.b, v);
+            S.istr[n] = NPL * SROW;
             S.idst[n++] = dst + 3 * SROW;
             if (P.unc) {
                 S.isrc[n] = plane(P.unc, P.u_bs, P.u_cs, G.b, v);
+                S.istr[n] = NPL * SROW;
                 S.idst[n++] = dst + 4 * SROW;
             }
         }
@@ -461,12 +469,14 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
             const int dst = ROW_OPP * SROW + SEG_PAD;
             for (int k = 0; k < 3; ++k) {
                 S.isrc[n] = plane(P.img, P.img_bs, P.img_cs, G.b, v * 3 + k);
+                S.istr[n] = NPO * SROW;
                 S.idst[n++] = dst + k * SROW;
             }
             S.isrc[n] = plane(P.disp, P.d_bs, P.d_cs, G.b, v);
+            S.istr[n] = NPO * SROW;
             S.idst[n++] = dst + 3 * SROW;
         }
-        for (; n < MAX_ISSUE; ++n) { S.isrc[n] = nullptr; S.idst[n] = 0; }
+        for (; n < MAX_ISSUE; ++n) { S.isrc[n] = nullptr; S.idst[n] = 0; S.istr[n] = 0; }
     }
 }
 
@@ -497,7 +507,7 @@ USL_HD void c_ring_issue(const LossParams& P, const CGeo& G, const CRings& S,
     __syncwarp();
 #endif
     if (row < 0 || lane >= n) return;
-    bulk_g2s(S.rows + S.idst[lane] + (size_t)slot * NPL * srow,
+    bulk_g2s(S.rows + S.idst[lane] + (size_t)slot * S.istr[lane],
              S.isrc[lane] + (long long)row * P.w, bytes, bar);
 }
 
@@ -529,7 +539,7 @@ USL_HD void c_ring_fill(const LossParams& P, const CGeo& G, const CState& T, int
     cp_f32(dst + 3 * SROW, P.disp + (T.o_d + ro));
     if (P.unc) cp_f32(dst + 4 * SROW, P.unc + (T.o_u + ro));
     if (MODE != MODE_TILED && G.nv == 1) {
-        float* od = T.sb + (ROW_OPP + slot * NPL) * SROW;
+        float* od = T.sb + (ROW_OPP + slot * NPO) * SROW;
         const float* oi = P.img + (T.o_oi + ro);
         cp_f32(od, oi);
         cp_f32(od + SROW, oi + P.img_cs);
@@ -652,8 +662,8 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
 
     // ---- reconstruction of the row: two taps of V at the shifted column ----
     float wd, dwd = 0.f, dI[3];
-    const float ix = c_warp_coord(T.xbase, sign * T.d, hw);
     {
+        const float ix = c_warp_coord(T.xbase, sign * T.d, hw);
         const float f = floorf(ix);
         const float w1 = ix - f, w0 = (f + 1.0f) - ix;
         const int xi = (int)fminf(fmaxf(f, -2.0f), fw);
@@ -700,11 +710,11 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
         }
         // ---- consistency terms ----
         // The transposed warp of both terms runs in cons_rows_kernel, lane per
-        // row; what it cannot recompute cheaply is the sign of (a - warp(b)), so
-        // the signed coefficients of the pixel are left behind, together with
-        // the two sampling columns (one 16-byte element per pixel: its rows then
-        // arrive there as bulk copies).
-        float s_dd = 0.f, s_ud = 0.f, ixu = 0.f;
+        // row; what it cannot recompute is the sign of (a - warp(b)) -- that
+        // needs the blended row -- so the signed coefficients s = coefficient *
+        // sign(.) of the pixel are left behind, with the two shifts beside them
+        // (both live in registers here: one coalesced 16-byte store per pixel).
+        float s_dd = 0.f, s_ud = 0.f;
         if (terms & TERM_CONS_D) {
             const float f = T.d - wd;
             T.acc[ACC_CONS_D] += own * fabsf(f);
@@ -714,7 +724,7 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
             }
         }
         if (terms & TERM_CONS_U) {
-            ixu = c_warp_coord(T.xbase, sign * T.u, hw);
+            const float ixu = c_warp_coord(T.xbase, sign * T.u, hw);
             const float f = floorf(ixu);
             const float w1 = ixu - f, w0 = (f + 1.0f) - ixu;
             const int xi = (int)fminf(fmaxf(f, -2.0f), fw);
@@ -728,7 +738,7 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
         }
         if (GRAD && P.scat && (!MASKED || own != 0.f))
             st_f4(reinterpret_cast<F4*>(P.scat) + (T.o_sc + (unsigned)(r * P.w)),
-                  ix, ixu, s_dd, s_ud);
+                  T.d, T.u, s_dd, s_ud);
         if (GRAD) { T.gd[0] = gdr; T.gu[0] = gur; }
     }
 

@@ -143,11 +143,13 @@ int col_launch_scale(const ColPlan* M, int i, bool grad, int skip_if_unit,
     return USL_ERR_UNSUPPORTED;
 }
 
-int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st) {
+int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st,
+               ColAfter after, void* after_ctx) {
     StreamPool* pool = (M->n > 1 && !knobs().col_serial) ? stream_pool() : nullptr;
     if (!pool) {
         for (int i = 0; i < M->n; ++i) {
-            const int rc = col_launch_scale(M, i, grad, skip_if_unit, st);
+            int rc = col_launch_scale(M, i, grad, skip_if_unit, st);
+            if (rc == USL_OK && after) rc = after(after_ctx, i, st);
             if (rc != USL_OK) return rc;
         }
         return USL_OK;
@@ -162,16 +164,19 @@ int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st) {
     if (hi) {
         if (cudaStreamWaitEvent(pool->first, pool->fork, 0) != cudaSuccess) return USL_ERR_CUDA;
         rc = col_launch_scale(M, 0, grad, skip_if_unit, pool->first);
+        if (rc == USL_OK && after) rc = after(after_ctx, 0, pool->first);
         if (cudaEventRecord(pool->join_first, pool->first) != cudaSuccess ||
             cudaStreamWaitEvent(st, pool->join_first, 0) != cudaSuccess)
             rc = rc == USL_OK ? USL_ERR_CUDA : rc;
     } else {
         rc = col_launch_scale(M, 0, grad, skip_if_unit, st);
+        if (rc == USL_OK && after) rc = after(after_ctx, 0, st);
     }
     for (int i = 1; i < M->n && rc == USL_OK; ++i) {
         cudaStream_t s = pool->side[i - 1];
         if (cudaStreamWaitEvent(s, pool->fork, 0) != cudaSuccess) { rc = USL_ERR_CUDA; break; }
         rc = col_launch_scale(M, i, grad, skip_if_unit, s);
+        if (rc == USL_OK && after) rc = after(after_ctx, i, s);
         // join even after a failed launch so that `st` stays well ordered
         if (cudaEventRecord(pool->join[i - 1], s) != cudaSuccess ||
             cudaStreamWaitEvent(st, pool->join[i - 1], 0) != cudaSuccess)

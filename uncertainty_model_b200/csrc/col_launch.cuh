@@ -47,6 +47,11 @@ int col_launch_scale(const ColPlan* M, int i, bool grad, int skip_if_unit,
 // Every scale of the plan: scale 0 on `st`, the others forked onto side streams
 // (they run concurrently and join `st` again); USL_COL_SERIAL=1 keeps all of
 // them on `st`.
-int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st);
+// `after` (optional): called right behind the launch of every scale, on that
+// scale's stream -- work that depends on one scale only (its transposed warp)
+// then runs while the other scales are still busy.
+typedef int (*ColAfter)(void* ctx, int scale, cudaStream_t stream);
+int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st,
+               ColAfter after = nullptr, void* after_ctx = nullptr);
 
 }  // namespace usl

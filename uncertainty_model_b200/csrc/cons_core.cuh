@@ -39,9 +39,8 @@ struct ConsParams {
     unsigned terms;                          // TERM_CONS_D | TERM_CONS_U
     float coef_dd, coef_ud;
     int R;                                   // strip height
-    const float* scat;                       // [b][view][h*w] x {ix_dd, ix_ud, s_dd, s_ud} from
-                                             // the column kernels (sampling columns, signed
-                                             // coefficients; s = 0 for a term that is off)
+    const float* scat;                       // LossParams::scat of the column kernels:
+                                             // [b][view][h*w] x {d, u, s_dd, s_ud}
 };
 
 struct ConsTile { int b, ya, yb; };

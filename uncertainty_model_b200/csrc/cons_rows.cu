@@ -16,17 +16,18 @@
 //
 // The price is one private row per lane (w + 5 floats): 64 lanes per SM at
 // w = 512, i.e. two walking warps whose pace is one dependent
-// load-add-store per step.  So everything that is not that chain is taken out
-// of it: the column kernels leave one 16-byte element {ix_dd, ix_ud, s_dd, s_ud} per
-// pixel behind (ConsParams::scat: the sampling columns of the two terms and
-// s = coef * upstream * sign(a - warp(b)), the one thing that cannot be
-// recomputed without the blended row) and the rows of
-// a 16-column tile arrive as bulk async copies (one per row, UBLKCP) on a
-// 4-stage mbarrier ring fed by the warps that do not walk; per 8 columns the
-// sampling columns, weights and addresses of both terms are computed first
-// (16 independent chains), then the 8 read-modify-writes run back to back, the
-// two terms of a column as ONE chain (loads, forwarding of the first term's
-// sums where the taps coincide, stores in order).
+// load-add-store per column.  So everything that is not that chain is taken out
+// of them.  The column kernels leave {d, u, s_dd, s_ud} per pixel behind
+// (ConsParams::scat: s = coef * upstream * sign(a - warp(b)) is the one thing
+// that cannot be recomputed without the blended row).  The warps of the CTA that
+// do not walk turn them, a tile of 16 columns ahead, into what the chain
+// consumes -- the tap contributions s * w0, s * w1 of both terms and the row
+// addresses of their first taps -- and hand them over through a 3-stage ring in
+// shared memory (mbarriers; a 336-byte block per row and tile, odd in 16-byte
+// units so that the column walk is bank-conflict free).  The walkers interleave
+// the read-modify-writes of 8 columns with the ring loads of the next 8, and
+// run the two terms of a column as ONE chain (loads, forwarding of the first
+// term's sums where the taps coincide, stores in order).
 //
 // CTA = destination rows [ya, yb) of one sample; lane t = rsi * 2 + v walks
 // source row rs0 + rsi of view v.  At the end all warps assemble the destination
@@ -40,12 +41,14 @@ namespace usl {
 
 constexpr int R4_THREADS = 256;
 constexpr int R4_TILE = 16;                 // columns per staged tile
-constexpr int R4_PITCH = R4_TILE + 1;       // 16-byte elements per staged row (odd: the
+constexpr int R4_PITCH = R4_TILE + 4 + 1;   // 16-byte elements per staged (row, tile) block:
+                                            // 16 contribution quadruples, 16 column pairs (odd: the
                                             // column walk is bank-conflict free)
-constexpr int R4_STAGES = 4;
+constexpr int R4_STAGES = 3;
 constexpr int R4_PAD = 2;                   // row = [2 | w | 2 (+1)]: taps outside the
                                             // image land in the pads
 constexpr int R4_BATCH = 8;
+constexpr int R4_MAXE = 11;                 // elements of a tile per preparing thread
 
 // floats per private row: odd, so that lanes at the same column (smooth
 // disparities) sit in 32 different banks
@@ -64,6 +67,8 @@ static R4Geo r4_geometry(int h, int w, size_t budget) {
     R4Geo g; g.nl = 0; g.R = 0; g.smem = 0;
     for (int nl = 128; nl >= 32; nl -= 32) {
         if (r4_smem(nl, w) > budget) continue;
+        // a preparing thread takes at most R4_MAXE of the nl * 16 elements of a tile
+        if (nl * R4_TILE > R4_MAXE * (((R4_THREADS - nl) / 64) * 32)) continue;
         // no point in more rows than the image has
         if (nl > 32 && (nl - 32) / 2 >= h) continue;
         g.nl = nl; g.smem = r4_smem(nl, w);
@@ -81,10 +86,6 @@ __device__ __forceinline__ uint32_t s_u32(const void* p) {
 __device__ __forceinline__ void mb_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                 ::"r"(s_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mb_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
 }
@@ -99,41 +100,29 @@ __device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
         "R4_DONE:\n"
         "}" ::"r"(s_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_row(void* dst, const void* src, uint32_t bytes,
-                                         uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+// c_warp_coord of col_core.cuh (same operations in the same order: the sampling
+// column comes out bit-identical to the one the column kernels used)
+__device__ __forceinline__ float r4_coord(float xbase, float shift, float half_n) {
+    const float x = xbase + shift;
+    const float g = fmaf(2.0f, x, -1.0f);
+    return fmaf(g + 1.0f, half_n, -0.5f);
 }
 
-// floor() and the float -> int conversion with additions only (F2I / FRND run
-// at a quarter of the rate, and a walking warp is alone on its scheduler):
-// adding 1.5 * 2^23 rounds to the nearest integer and leaves it in the low
-// mantissa bits; |x| < 2^22 here (columns).
-constexpr float R4_MAGIC = 12582912.0f;
-__device__ __forceinline__ float r4_floor(float x) {
-    const float r = (x + R4_MAGIC) - R4_MAGIC;      // nearest integer
-    return r > x ? r - 1.0f : r;
-}
-__device__ __forceinline__ int r4_int(float integral) {
-    return __float_as_int(integral + R4_MAGIC) - 0x4B400000;
-}
-
-// column offset (from column 0 of the row) and the two tap contributions of a
-// pixel with sampling column ix and signed coefficient s
-__device__ __forceinline__ void r4_decode(float ix, float s, float fw, int& off,
-                                          float& c0, float& c1) {
-    const float f = r4_floor(ix);
+// first tap column + 2 (columns -2 .. w+1 exist in a row: taps outside the image
+// land in pads nobody reads) and the two tap contributions of a pixel
+__device__ __forceinline__ void r4_decode(float xb, float shift, float s, float hwf,
+                                          float fw, unsigned& col, float& c0, float& c1) {
+    const float ix = r4_coord(xb, shift, hwf);
+    const float f = floorf(ix);
     const float w1 = ix - f, w0 = (f + 1.0f) - ix;
-    // columns -2 .. w+1 exist: taps outside the image land in pads nobody reads
-    off = r4_int(fminf(fmaxf(f, -2.0f), fw));
+    col = (unsigned)((int)fminf(fmaxf(f, -2.0f), fw) + 2);
     c0 = s * w0;
     c1 = s * w1;
 }
 
-struct R4Batch {
-    int od[R4_BATCH], ou[R4_BATCH];
-    float cd0[R4_BATCH], cd1[R4_BATCH], cu0[R4_BATCH], cu1[R4_BATCH];
+struct R4Batch {            // 8 columns: tap contributions and row addresses
+    float4 c[R4_BATCH];     // {dd tap 0, dd tap 1, ud tap 0, ud tap 1}
+    uint32_t pd[R4_BATCH], pu[R4_BATCH];   // shared-window addresses of the first taps
 };
 
 __global__ void __launch_bounds__(R4_THREADS, 1)
@@ -167,147 +156,158 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
 
     for (int i = tid; i < nl * HW; i += R4_THREADS) H[i] = 0.0f;
     // rows past the strip are never copied: their lanes must read zeros
+    // (contributions 0 into column -2, a pad)
     for (int i = tid; i < R4_STAGES * nl * R4_PITCH; i += R4_THREADS)
         stage[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
     if (tid == 0) {
-        // (every feeding warp that holds rows arrives once per tile, with its bytes)
-        const int nrows0 = (rs1 - rs0 + 1) * 2;
-        const int feeders = min((nrows0 + 31) / 32, R4_THREADS / 32 - nwalk);
-        for (int k = 0; k < R4_STAGES; ++k) { mb_init(full + k, feeders); mb_init(empty + k, nwalk); }
+        // (every preparing warp arrives once per tile, every walking warp releases it)
+        for (int k = 0; k < R4_STAGES; ++k) {
+            mb_init(full + k, (R4_THREADS / 32 - nwalk) / 2);
+            mb_init(empty + k, nwalk);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     if (warp >= nwalk) {
-        // ---- the feeding warps: one bulk copy per (row, view) and tile; a copy
-        // is issued by one lane at a time (UBLKCP takes uniform operands), so the
-        // rows are dealt out over all the warps that do not walk, one per lane --
-        const int nrows = (rs1 - rs0 + 1) * 2;
-        const int t = tid - nl;                           // this lane's row, if any
-        const bool mine = t < nrows;
-        const unsigned active = __ballot_sync(0xffffffffu, mine);
-        if (active) {
-            const int rs = rs0 + (t >> 1), v = t & 1;
-            const float4* src = reinterpret_cast<const float4*>(P.scat) +
-                                ((long long)b * 2 + v) * hw + (long long)rs * w;
-            const int mycount = __popc(active);
-            for (int k = 0; k < ntile; ++k) {
+        // ---- the preparing warps: {d, u, s_dd, s_ud} of a tile (16 columns of
+        // every row) -> tap contributions + tap columns in the ring.  Two groups
+        // of warps take alternate tiles: a thread loads its elements, waits for
+        // them, decodes, stores -- while it waits on memory the other group
+        // works.  (Prefetching the next tile into registers instead does not
+        // overlap anything: the wait for this tile's loads drains the same
+        // scoreboard the new loads were just put on.)  Consecutive threads take
+        // consecutive columns of a row: coalesced 16-byte loads.
+        const int npw = ((R4_THREADS / 32 - nwalk) / 2) * 2;   // warps used: two equal groups
+        const int pw = warp - nwalk;
+        if (pw < npw) {
+            const int g = pw & 1, gt = (pw >> 1) * 32 + lane, gn = (npw / 2) * 32;
+            const int nrows = (rs1 - rs0 + 1) * 2;
+            const int nelem = nrows * R4_TILE;             // per tile
+            const float fw = (float)w, hwf = 0.5f * fw;
+            const float4* src0 = reinterpret_cast<const float4*>(P.scat) + (long long)b * 2 * hw;
+            for (int k = g; k < ntile; k += 2) {
                 const int st = k % R4_STAGES;
+                float4 q[R4_MAXE];
+#pragma unroll
+                for (int i = 0; i < R4_MAXE; ++i) {
+                    const int e = gt + i * gn;
+                    const int t = e / R4_TILE, x = k * R4_TILE + (e % R4_TILE);
+                    q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e < nelem && x < w)
+                        q[i] = __ldg(src0 + (long long)(t & 1) * hw +
+                                     (long long)(rs0 + (t >> 1)) * w + x);
+                }
                 if (k >= R4_STAGES) mb_wait(empty + st, ((k / R4_STAGES) - 1) & 1);
-                const int c0 = k * R4_TILE;
-                const uint32_t bytes = (uint32_t)min(R4_TILE, w - c0) * 16u;
-                if (lane == 0) mb_expect_tx(full + st, bytes * (uint32_t)mycount);
+#pragma unroll
+                for (int i = 0; i < R4_MAXE; ++i) {
+                    const int e = gt + i * gn;
+                    if (e >= nelem) continue;
+                    const int t = e / R4_TILE, j = e % R4_TILE;
+                    const float sign = (t & 1) ? 1.0f : -1.0f;
+                    const float xb = linspace01(k * R4_TILE + j, w);
+                    unsigned cd, cu;
+                    float4 c;
+                    r4_decode(xb, sign * q[i].x, q[i].z, hwf, fw, cd, c.x, c.y);
+                    r4_decode(xb, sign * q[i].y, q[i].w, hwf, fw, cu, c.z, c.w);
+                    float4* blk = stage + ((size_t)st * nl + t) * R4_PITCH;
+                    blk[j] = c;
+                    reinterpret_cast<unsigned*>(blk + R4_TILE)[j] = cd | (cu << 16);
+                }
                 __syncwarp();
-                if (mine)
-                    bulk_row(stage + ((size_t)st * nl + t) * R4_PITCH, src + c0, bytes,
-                             full + st);
+                if (lane == 0) mb_arrive(full + st);
             }
         }
     } else if (warp < nwalk) {
         // ---- the walk ---------------------------------------------------------
         // Software pipeline over batches of 8 columns: the read-modify-writes
-        // of batch i are interleaved, instruction by instruction, with the
-        // staged loads and the decoding of batch i + 1 (independent work that
-        // fills the load-add-store bubbles of the one dependent chain).
-        float* Hrow = H + (size_t)tid * HW + R4_PAD;
-        const float fw = (float)w;
-        constexpr int BPT = R4_TILE / R4_BATCH;              // batches per tile
+        // of batch i are interleaved with the staged loads of batch i + 1.
+        const uint32_t row_a = s_u32(H + (size_t)tid * HW);   // column -2 of the row
+        constexpr int BPT = R4_TILE / R4_BATCH;               // batches per tile
         const int nbatch = (w + R4_BATCH - 1) / R4_BATCH;
 
-        // staged loads + decode of batch `bi` (waits for its tile first;
-        // releases the tile after its last batch)
-        // (a term that is off has s = 0)
-        auto decode = [&](int bi, R4Batch& D, int u) {
+        // staged loads of batch `bi`: tap contributions, tap columns -> addresses
+        auto load = [&](int bi, R4Batch& D) {
             const int k = bi / BPT, st = k % R4_STAGES;
-            const int j = (bi - k * BPT) * R4_BATCH + u;
-            const float4 q = stage[((size_t)st * nl + tid) * R4_PITCH + j];
-            r4_decode(q.x, q.z, fw, D.od[u], D.cd0[u], D.cd1[u]);
-            r4_decode(q.y, q.w, fw, D.ou[u], D.cu0[u], D.cu1[u]);
+            const int j = (bi - k * BPT) * R4_BATCH;
+            const float4* blk = stage + ((size_t)st * nl + tid) * R4_PITCH;
+            const float4* a = blk + j;
+            const uint4* o = reinterpret_cast<const uint4*>(blk + R4_TILE) + j / 4;
+            const uint4 o0 = o[0], o1 = o[1];
+            const uint32_t ow[R4_BATCH] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+            for (int u = 0; u < R4_BATCH; ++u) {
+                D.c[u] = a[u];
+                D.pd[u] = row_a + 4u * (ow[u] & 0xffffu);
+                D.pu[u] = row_a + 4u * (ow[u] >> 16);
+            }
         };
         auto acquire = [&](int bi) {
-            if (bi < nbatch && bi % BPT == 0) {
+            if (bi % BPT == 0) {
                 const int k = bi / BPT;
                 mb_wait(full + k % R4_STAGES, (k / R4_STAGES) & 1);
             }
         };
         auto release = [&](int bi) {
-            if (bi < nbatch && (bi % BPT == BPT - 1 || bi == nbatch - 1)) {
+            if (bi % BPT == BPT - 1 || bi == nbatch - 1) {
                 __syncwarp();
                 if (lane == 0) mb_arrive(empty + (bi / BPT) % R4_STAGES);
             }
         };
-        // both terms of a column as ONE chain: all loads, the sums of term dd
-        // forwarded where the taps of term ud coincide with them, stores in order
-        // (explicit shared-memory instructions: the four loads must all be
-        //  issued before the arithmetic -- left to itself the compiler sinks
-        //  the second pair behind a branch on `diff`, two round trips a column)
-        const uint32_t hrow_a = s_u32(Hrow);
+        // Both terms of a column as ONE chain: all loads, the sums of term dd
+        // forwarded where the taps of term ud coincide with them, stores in
+        // order.  (Explicit shared-memory instructions: the four loads must all
+        // be issued before the arithmetic -- left to itself the compiler sinks
+        // the second pair behind a branch, two round trips a column.)
         auto rmw = [&](const R4Batch& D, int u) {
-            const uint32_t pd = hrow_a + 4u * (uint32_t)D.od[u];
-            const uint32_t pu = hrow_a + 4u * (uint32_t)D.ou[u];
+            const uint32_t pd = D.pd[u], pu = D.pu[u];
             float d0, d1, u0, u1;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d0) : "r"(pd));
             asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(d1) : "r"(pd));
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(u0) : "r"(pu));
             asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(u1) : "r"(pu));
-            const int diff = D.ou[u] - D.od[u];
-            d0 -= D.cd0[u]; d1 -= D.cd1[u];
+            const int diff = (int)(pu - pd);
+            d0 -= D.c[u].x; d1 -= D.c[u].y;
             u0 = diff == 0 ? d0 : u0;
-            u0 = diff == 1 ? d1 : u0;
+            u0 = diff == 4 ? d1 : u0;
             u1 = diff == 0 ? d1 : u1;
-            u1 = diff == -1 ? d0 : u1;
-            u0 -= D.cu0[u]; u1 -= D.cu1[u];
+            u1 = diff == -4 ? d0 : u1;
+            u0 -= D.c[u].z; u1 -= D.c[u].w;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(pd), "f"(d0));
             asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(pd), "f"(d1));
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(pu), "f"(u0));
             asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(pu), "f"(u1));
         };
-        // full batches run in the pipeline; a last partial one (row width not a
-        // multiple of 8: its slot holds stale elements past the end of the row)
-        // is decoded with a guard and scattered on its own
-        const int nfull = w / R4_BATCH;
+        // (columns past the end of a row were filled with zero contributions)
         R4Batch A, B;
-        if (nfull > 0) {
-            acquire(0);
-#pragma unroll
-            for (int u = 0; u < R4_BATCH; ++u) decode(0, A, u);
-            release(0);
-        }
+        acquire(0);
+        load(0, A);
+        release(0);
 #pragma unroll 1
-        for (int bi = 0; bi < nfull; bi += 2) {
-            if (bi + 1 < nfull) {
+        for (int bi = 0; bi < nbatch; bi += 2) {
+            if (bi + 1 < nbatch) {
                 acquire(bi + 1);
+                load(bi + 1, B);
 #pragma unroll
-                for (int u = 0; u < R4_BATCH; ++u) { rmw(A, u); decode(bi + 1, B, u); }
+                for (int u = 0; u < R4_BATCH; ++u) rmw(A, u);
                 release(bi + 1);
             } else {
 #pragma unroll
                 for (int u = 0; u < R4_BATCH; ++u) rmw(A, u);
                 break;
             }
-            if (bi + 2 < nfull) {
+            if (bi + 2 < nbatch) {
                 acquire(bi + 2);
+                load(bi + 2, A);
 #pragma unroll
-                for (int u = 0; u < R4_BATCH; ++u) { rmw(B, u); decode(bi + 2, A, u); }
+                for (int u = 0; u < R4_BATCH; ++u) rmw(B, u);
                 release(bi + 2);
             } else {
 #pragma unroll
                 for (int u = 0; u < R4_BATCH; ++u) rmw(B, u);
             }
-        }
-        if (nfull < nbatch) {
-            acquire(nfull);
-#pragma unroll 1
-            for (int u = 0; u < w - nfull * R4_BATCH; ++u) {
-                const int k = nfull / BPT, st = k % R4_STAGES;
-                const int j = (nfull - k * BPT) * R4_BATCH + u;
-                const float4 q = stage[((size_t)st * nl + tid) * R4_PITCH + j];
-                r4_decode(q.x, q.z, fw, A.od[0], A.cd0[0], A.cd1[0]);
-                r4_decode(q.y, q.w, fw, A.ou[0], A.cu0[0], A.cu1[0]);
-                rmw(A, 0);
-            }
-            release(nfull);
         }
     }
     __syncthreads();
@@ -361,16 +361,18 @@ int cons_rows_launch(MultiCons* C, cudaStream_t st) {
         ConsParams& c = C->P[k];
         if (!c.scat || ((uintptr_t)c.scat & 15)) return USL_ERR_ARG;
         const R4Geo g = r4_geometry(c.h, c.w, 210 * 1024);
-        if (!g.nl || 2 * g.nl > R4_THREADS) return USL_ERR_UNSUPPORTED;   // one feeding lane per row
+        if (!g.nl) return USL_ERR_UNSUPPORTED;
         c.R = g.R;
         C->lanes[k] = g.nl;
         C->strips[k] = (c.h + c.R - 1) / c.R;
         C->cta_start[k + 1] = C->cta_start[k] + C->strips[k] * c.B;
         if (g.smem > smem) smem = g.smem;
     }
+    // (the limit, not this launch's need: launches of several scales are in
+    //  flight on different streams)
     if (cudaFuncSetAttribute(cons_rows_kernel,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem) != cudaSuccess)
+                             210 * 1024) != cudaSuccess)
         return USL_ERR_CUDA;
     cons_rows_kernel<<<C->cta_start[C->n], R4_THREADS, smem, st>>>(*C);
     return check_launch();

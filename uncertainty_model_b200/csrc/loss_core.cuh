@@ -89,9 +89,8 @@ struct LossParams {
     float* grad_recon_out;       // (B,6,h,w) contiguous when recon is given
     int grad_disp_accumulate;    // add to what the scatter kernel stored
     // input of the lane-per-row transposed warp of the consistency terms
-    // (column kernels -> cons_rows_kernel): [b][view][h*w] elements
-    // {sampling column of term dd, of term ud, coefficient * sign(a - warp(b))
-    // of term dd, of term ud}, or NULL
+    // (column kernels -> cons_rows_kernel), or NULL: [b][view][h*w] x
+    // {d, u, s of term dd, s of term ud}, s = coefficient * sign(a - warp(b))
     float* scat;
     // ---- configuration
     unsigned terms;

@@ -334,7 +334,8 @@ extern "C" int usl_loss_fwd_ctas(const UslLossScale* s) {
 static int try_col(const UslLossConfig* cfgs, const UslLossScale* scales,
                    int n, bool grad, float* partials, const float* gout_d,
                    const float* gout_e, int accumulate, int skip_if_unit,
-                   cudaStream_t st, int* rc_out) {
+                   cudaStream_t st, int* rc_out, ColAfter after = nullptr,
+                   void* after_ctx = nullptr) {
     if (!col_eligible(cfgs, scales, n)) return 0;
     ColPlan M;
     M.n = n;
@@ -351,7 +352,7 @@ static int try_col(const UslLossConfig* cfgs, const UslLossScale* scales,
             (accumulate && (p.terms & (TERM_CONS_D | TERM_CONS_U))) ? 1 : 0;
         if (grad && (!p.grad_disp || !p.grad_unc)) { *rc_out = USL_ERR_ARG; return 1; }
     }
-    *rc_out = col_launch(&M, grad, skip_if_unit, st);
+    *rc_out = col_launch(&M, grad, skip_if_unit, st, after, after_ctx);
     return 1;
 }
 
@@ -419,13 +420,14 @@ static int launch_scatter(const LossParams* P, int n_scales,
                           const float* gout_disp, const float* gout_err,
                           float gout_default, int skip_if_unit, bool launch,
                           cudaStream_t st, int* rc_out, int accumulate = 0,
-                          bool scat_filled = false) {
+                          bool scat_filled = false, int only_scale = -1) {
     MultiCons C;
     C.n = 0; C.cta_start[0] = 0; C.skip_if_unit = skip_if_unit;
     size_t csmem = 0;
     bool use_scat = scat_filled && !knobs().exp[0];
     for (int i = 0; i < n_scales; ++i) {
         const LossParams& p = P[i];
+        if (only_scale >= 0 && i != only_scale) continue;
         if (!(p.terms & (TERM_CONS_D | TERM_CONS_U))) continue;
         if (!p.grad_disp) { *rc_out = USL_ERR_ARG; return 0; }
         ConsParams c = {};
@@ -479,6 +481,19 @@ static int launch_scatter(const LossParams* P, int n_scales,
     return C.n;
 }
 
+struct AfterScale {
+    const LossParams* P; int n;
+    const float* gout_disp; const float* gout_err;
+    int skip;
+};
+static int scatter_after_scale(void* ctx_, int scale, cudaStream_t st) {
+    const AfterScale* c = static_cast<const AfterScale*>(ctx_);
+    int rc = USL_OK;
+    launch_scatter(c->P, c->n, c->gout_disp, c->gout_err, 1.0f, c->skip, true, st, &rc,
+                   1, true, scale);
+    return rc;
+}
+
 extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
                              const UslLossScale* scales, int n_scales,
                              const float* gout_disp, const float* gout_err,
@@ -492,6 +507,22 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
     const int skip = (flags & USL_GRAD_SKIP_IF_UNIT) ? 1 : 0;
     // column kernels: they store the gradient, then the scatter adds its part
     // (the read-modify-write sits in the kernel that has warps to spare)
+    if (!(flags & (USL_GRAD_ONLY_SCATTER | USL_GRAD_NO_SCATTER)) && !knobs().exp[1]) {
+        // both halves: the scatter of every scale right behind its own fused
+        // kernel, on that scale's stream -- the small scales' finish in the
+        // shadow of the largest scale's fused kernel
+        bool rows_ok = true;
+        for (int i = 0; i < n_scales; ++i)
+            rows_ok = rows_ok && (!(P[i].terms & (TERM_CONS_D | TERM_CONS_U)) || P[i].scat);
+        if (rows_ok) {
+            AfterScale ctx = {P, n_scales, gout_disp, gout_err, skip};
+            if (!try_col(cfgs, scales, n_scales, true, partials, gout_disp,
+                         gout_err, 0, skip, (cudaStream_t)stream, &rc,
+                         scatter_after_scale, &ctx))
+                return USL_ERR_UNSUPPORTED;
+            return rc;
+        }
+    }
     if (!(flags & USL_GRAD_ONLY_SCATTER)) {
         if (!try_col(cfgs, scales, n_scales, true, partials, gout_disp,
                      gout_err, 0, skip, (cudaStream_t)stream, &rc))
