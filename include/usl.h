@@ -22,8 +22,9 @@
  *   - return value: USL_OK or a negative UslError; never throws, never exits.
  *   - re-entrant.  State: tables that are written once and immutable
  *     afterwards (tuning knobs read from the environment at first use, SM
- *     counts) and, per host thread and device, a small pool of side streams
- *     and events for the concurrent per-scale launches.
+ *     counts), a launch counter (usl_launch_count) and, per host thread and
+ *     device, a small pool of side streams and events for the concurrent
+ *     per-scale launches.
  */
 #ifndef USL_H_
 #define USL_H_
@@ -49,6 +50,8 @@ typedef enum UslError {
 
 int usl_version(void);
 const char* usl_strerror(int rc);
+/* kernel launches this process has issued through the library so far */
+long long usl_launch_count(void);
 
 /* ---- train/utils.py:27-50  scale_pyramid ---------------------------------
  * src (B,C,H,W).  dst[i], i = 1..scales-1, contiguous (B,C,H>>i,W>>i);
@@ -189,6 +192,54 @@ int usl_loss_bwd(const UslLossConfig* cfgs, const UslLossScale* scales,
 int usl_loss_grad(const UslLossConfig* cfgs, const UslLossScale* scales,
                   int n_scales, const float* gout_disp, const float* gout_err,
                   float* partials, int flags, void* stream);
+
+/* The gradients usl_loss_grad wrote are those for unit upstream gradients, and
+ * they are linear in the upstream pair.  When BOTH outputs receive the SAME
+ * upstream gradient g (the training loop back-propagates disp_loss +
+ * error_loss, reference train.py:126-128; a loss scaler multiplies that sum)
+ * the backward is this one launch: every buffer is multiplied by *g in place,
+ * and nothing at all is touched when *g == 1 (decided on the device: no host
+ * synchronisation).  buffers / counts: HOST arrays of n device pointers and
+ * element counts. */
+#define USL_MAX_RESCALE 16
+int usl_grad_rescale(const float* g, float* const* buffers,
+                     const long long* counts, int n, void* stream);
+
+/* ---- model/layers/decoder.py:239-246  disparity head ---------------------
+ * pred = scale * sigmoid(logits) for every pyramid level in one launch, and
+ * its backward grad_logits = grad_pred * pred * (1 - pred / scale).  HOST
+ * arrays of `levels` device pointers / element counts. */
+int usl_head_fwd(const float* const* logits, float* const* pred,
+                 const long long* counts, int levels, float scale, void* stream);
+int usl_head_bwd(const float* const* grad_pred, const float* const* pred,
+                 float* const* grad_logits, const long long* counts, int levels,
+                 float scale, void* stream);
+
+/* ---- train/utils.py:53-62,138-140,248-273  discriminator input ------------
+ * out (2B,6,h,w) of every level = [image level ; its reconstruction] along the
+ * batch axis, one launch for all levels: the reconstruction half is warped on
+ * the fly from `pred` (channels 0, 1 = d_L, d_R; utils.py:112-135) -- the
+ * reconstruction pyramid is never materialised -- or, with pred = NULL,
+ * copied from a materialised `recon` level. */
+typedef struct UslDiscLevel {
+    int32_t B, h, w, reserved;
+    const float* images; int64_t img_bs, img_cs;   /* (B,6,h,w) */
+    const float* pred;   int64_t pred_bs, pred_cs; /* (B,>=2,h,w) or NULL */
+    const float* recon;  int64_t rec_bs, rec_cs;   /* (B,6,h,w) when pred is NULL */
+    float* out;                                    /* contiguous (2B,6,h,w) */
+} UslDiscLevel;
+int usl_disc_input(const UslDiscLevel* levels, int n_levels, void* stream);
+
+/* ---- train/utils.py:199-245  combine_disparity ----------------------------
+ * left, right: contiguous fp32 (planes,h,w); out fp64 like the numpy original. */
+int usl_combine_disparity(const float* left, const float* right, int planes,
+                          int h, int w, double alpha, double beta, double* out,
+                          void* stream);
+/* ---- train/utils.py:177-196  to_heatmap -----------------------------------
+ * x: n fp32 values; lut: device fp64 [entries][3] (the colour map's table);
+ * out fp64 (3, n).  matplotlib's Colormap.__call__ indexing. */
+int usl_heatmap(const float* x, long long n, int inverse, const double* lut,
+                int entries, double* out, void* stream);
 
 /* 3x3 valid mean (loss.py:386-387, `pooling=True`) and its transpose. */
 int usl_pool3_fwd(const float* x, long long x_bs, long long x_cs, int B, int C,

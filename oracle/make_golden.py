@@ -210,6 +210,17 @@ def spars_cases(S):
     print('spars written, c5 ause', float(out['c5_4frames_ause']))
 
 
+def post_case(u):
+    """train/utils.py:199-245 (combine_disparity: numpy only, runs as is)."""
+    g = torch.Generator().manual_seed(21)
+    left = 0.3 * torch.rand(1, 48, 80, generator=g)
+    right = 0.3 * torch.rand(1, 48, 80, generator=g)
+    out = u.combine_disparity(left, right)
+    np.savez_compressed(os.path.join(GOLDEN, 'post.npz'), left=left.numpy(),
+                        right=right.numpy(), combined=out.numpy())
+    print('post written')
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(GOLDEN, exist_ok=True)
@@ -230,6 +241,7 @@ def main():
     component_case(L, u)
     anchors(L, u)
     spars_cases(S)
+    post_case(u)
 
 
 if __name__ == '__main__':

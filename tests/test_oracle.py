@@ -236,3 +236,23 @@ def test_kink_mask_margins_and_explicit_warp():
     # ... and would not pass untrimmed: the masked elements carry the error
     assert max(s['full'] for s in stats) > 10 * parity.GRAD_REL
     assert max(s['masked'] for s in stats) < 2e-3
+
+
+# ------------------------------------------------- post-processing ports ----
+def test_combine_disparity_port_matches_reference_fixture():
+    from oracle import post_port as PP
+    g = load('post.npz')
+    out = PP.combine_disparity(torch.from_numpy(g['left']),
+                               torch.from_numpy(g['right']))
+    assert out.dtype == torch.float64
+    assert np.array_equal(out.numpy(), g['combined'])
+
+
+def test_heatmap_port_indexing_rule():
+    """matplotlib is absent here: the restated Colormap.__call__ rule on the
+    values that exercise every branch of it."""
+    from oracle import post_port as PP
+    table = np.arange(256 * 3, dtype=np.float64).reshape(256, 3)
+    x = torch.tensor([[[0.0, 1.0, -0.1, 2.0, float('nan'), 0.5, 255.0 / 256]]])
+    out = PP.to_heatmap(x, table)[0].numpy().ravel()      # R channel = 3 * index
+    assert list(out) == [0.0, 765.0, 0.0, 765.0, 0.0, 384.0, 765.0]

@@ -13,6 +13,7 @@ USL_NUM_TERMS = 6
 USL_MAX_SCALES = 8
 USL_ERR_UNSUPPORTED = -3
 USL_SCALE_GENERAL_KERNELS = 1
+USL_MAX_RESCALE = 16
 
 TERM_REPROJ, TERM_CONS_D, TERM_SMOOTH_D = 1, 2, 4
 TERM_UNC, TERM_SMOOTH_U, TERM_CONS_U = 8, 16, 32
@@ -45,10 +46,22 @@ class UslLossScale(C.Structure):
     ]
 
 
+class UslDiscLevel(C.Structure):
+    _fields_ = [
+        ('B', C.c_int32), ('h', C.c_int32), ('w', C.c_int32),
+        ('reserved', C.c_int32),
+        ('images', _f32p), ('img_bs', C.c_int64), ('img_cs', C.c_int64),
+        ('pred', _f32p), ('pred_bs', C.c_int64), ('pred_cs', C.c_int64),
+        ('recon', _f32p), ('rec_bs', C.c_int64), ('rec_cs', C.c_int64),
+        ('out', _f32p),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/usl.h one to one
 SIGNATURES = {
     'usl_version': (C.c_int, []),
     'usl_strerror': (C.c_char_p, [C.c_int]),
+    'usl_launch_count': (C.c_longlong, []),
     'usl_pyramid': (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_longlong, C.c_longlong, C.c_int,
                               C.POINTER(C.c_void_p), C.c_void_p]),
@@ -78,6 +91,22 @@ SIGNATURES = {
     'usl_loss_bwd': (C.c_int, [C.POINTER(UslLossConfig),
                                C.POINTER(UslLossScale), C.c_int, _f32p, _f32p,
                                C.c_int, C.c_void_p]),
+    'usl_grad_rescale': (C.c_int, [_f32p, C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_longlong), C.c_int,
+                                   C.c_void_p]),
+    'usl_head_fwd': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_longlong), C.c_int, C.c_float,
+                               C.c_void_p]),
+    'usl_head_bwd': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
+                               C.c_int, C.c_float, C.c_void_p]),
+    'usl_disc_input': (C.c_int, [C.POINTER(UslDiscLevel), C.c_int,
+                                 C.c_void_p]),
+    'usl_combine_disparity': (C.c_int, [_f32p, _f32p, C.c_int, C.c_int,
+                                        C.c_int, C.c_double, C.c_double,
+                                        C.c_void_p, C.c_void_p]),
+    'usl_heatmap': (C.c_int, [_f32p, C.c_longlong, C.c_int, C.c_void_p,
+                              C.c_int, C.c_void_p, C.c_void_p]),
     'usl_pool3_fwd': (C.c_int, [_f32p, C.c_longlong, C.c_longlong, C.c_int,
                                 C.c_int, C.c_int, C.c_int, _f32p,
                                 C.c_void_p]),

@@ -46,6 +46,26 @@ pool3_bwd_kernel(const float* go, int B, int C, int h, int w, float* gx) {
     }
 }
 
+// buffers[i][0 .. counts[i]) *= *g unless *g == 1 (see usl_grad_rescale)
+struct RescaleArgs {
+    float* buf[USL_MAX_RESCALE];
+    long long end[USL_MAX_RESCALE];    // running sum of the element counts
+    int n;
+};
+__global__ void __launch_bounds__(256)
+rescale_kernel(const float* g, const __grid_constant__ RescaleArgs A) {
+    const float s = __ldg(g);
+    if (s == 1.0f) return;
+    const long long total = A.end[A.n - 1];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int k = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += stride) {
+        while (i >= A.end[k]) ++k;
+        A.buf[k][i - (k ? A.end[k - 1] : 0)] *= s;
+    }
+}
+
 static unsigned grid_for(long long total) {
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
@@ -57,6 +77,10 @@ static unsigned grid_for(long long total) {
 }  // namespace usl
 
 extern "C" int usl_version(void) { return USL_VERSION; }
+
+extern "C" long long usl_launch_count(void) {
+    return usl::launch_counter().load(std::memory_order_relaxed);
+}
 
 extern "C" const char* usl_strerror(int rc) {
     switch (rc) {
@@ -89,5 +113,23 @@ extern "C" int usl_pool3_bwd(const float* grad_out, int B, int C, int h, int w,
     const long long total = (long long)B * C * h * w;
     usl::pool3_bwd_kernel<<<usl::grid_for(total), 256, 0, (cudaStream_t)stream>>>(
         grad_out, B, C, h, w, grad_x);
+    return usl::check_launch();
+}
+
+extern "C" int usl_grad_rescale(const float* g, float* const* buffers,
+                                const long long* counts, int n, void* stream) {
+    if (!g || !buffers || !counts || n < 1 || n > USL_MAX_RESCALE) return USL_ERR_ARG;
+    usl::DeviceGuard guard(g);
+    usl::RescaleArgs A;
+    long long total = 0;
+    A.n = n;
+    for (int i = 0; i < n; ++i) {
+        if (!buffers[i] || counts[i] < 0) return USL_ERR_ARG;
+        total += counts[i];
+        A.buf[i] = buffers[i];
+        A.end[i] = total;
+    }
+    if (total == 0) return USL_OK;
+    usl::rescale_kernel<<<usl::grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, A);
     return usl::check_launch();
 }

@@ -12,7 +12,15 @@
 
 namespace usl {
 
+// Kernel launches issued by the library so far (usl_launch_count: bench.py
+// reports the launches of a step from it instead of claiming a constant).
+inline std::atomic<long long>& launch_counter() {
+    static std::atomic<long long> n{0};
+    return n;
+}
+
 inline int check_launch() {
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return (e == cudaSuccess) ? USL_OK : USL_ERR_CUDA;
 }

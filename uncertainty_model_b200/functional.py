@@ -294,6 +294,16 @@ def loss_regrad(arrays, n_scales: int, g_disp: Tensor, g_err: Tensor,
                               stream), 'usl_loss_grad')
 
 
+def grad_rescale(g: Tensor, buffers: Sequence[Tensor], device) -> None:
+    """buffers *= g in place unless g == 1 (include/usl.h: usl_grad_rescale)."""
+    n = len(buffers)
+    ptrs = (C.c_void_p * n)(*[b.data_ptr() for b in buffers])
+    counts = (C.c_longlong * n)(*[b.numel() for b in buffers])
+    check(lib().usl_grad_rescale(
+        g.data_ptr(), ptrs, counts, n,
+        torch.cuda.current_stream(device).cuda_stream), 'usl_grad_rescale')
+
+
 def pyramid(x: Tensor, scales: int) -> List[Tensor]:
     """train/utils.py:27-50.  Level 0 is `x` itself (the reference's level 0
     is a bit-identical copy); levels >= 1 come from one launch."""
@@ -596,10 +606,18 @@ class FusedLoss(torch.autograd.Function):
             ctx.backward_calls += 1
             if ctx.backward_calls == 1:
                 # the buffers hold the gradients for unit upstream gradients
-                # (written by the forward): redone in place only if (gd, ge)
-                # differ from (1, 1) -- decided on the device
+                # (written by the forward)
                 grads = ctx.onepass
-                loss_regrad(ctx.arrays, len(specs), gd, ge, device, True)
+                live = [g for g in grads if g is not None]
+                if gd.data_ptr() == ge.data_ptr() and \
+                        len(live) <= _lib.USL_MAX_RESCALE:
+                    # one upstream gradient for both outputs -- what
+                    # (disp_loss + error_loss).backward() hands over: scale in
+                    # place unless it is 1 (decided on the device), one launch
+                    grad_rescale(gd, live, device)
+                else:
+                    # redone in place if (gd, ge) differ from (1, 1)
+                    loss_regrad(ctx.arrays, len(specs), gd, ge, device, True)
             else:
                 # backward(retain_graph=True) again: the first call's buffers
                 # were handed to autograd (and may hold non-unit gradients
@@ -628,3 +646,84 @@ def _spec_shape(sp: ScaleSpec, tensors) -> Tuple[int, int, int]:
             b, _, h, w = tensors[idx].shape
             return b, h, w
     raise ValueError('empty scale spec')
+
+
+# --------------------------------------------------------------------------
+# either side of the loss path
+# --------------------------------------------------------------------------
+def _ptr_array(tensors: Sequence[Tensor]):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _count_array(tensors: Sequence[Tensor]):
+    return (C.c_longlong * len(tensors))(*[t.numel() for t in tensors])
+
+
+class DisparityHead(torch.autograd.Function):
+    """The decoder's output activation over a whole pyramid (reference
+    model/layers/decoder.py:239-246): pred_i = scale * sigmoid(logits_i), every
+    level in one launch, forward and backward."""
+
+    @staticmethod
+    def forward(ctx, scale: float, *logits: Tensor):
+        for i, t in enumerate(logits):
+            require_cuda_f32(t, f'logits {i}')
+        if not 0 < len(logits) <= _lib.USL_MAX_SCALES:
+            raise ValueError(f'1 to {_lib.USL_MAX_SCALES} levels')
+        if not scale > 0:
+            raise ValueError('scale must be positive')
+        logits = [t.contiguous() for t in logits]
+        preds = [torch.empty_like(t) for t in logits]
+        check(lib().usl_head_fwd(_ptr_array(logits), _ptr_array(preds),
+                                 _count_array(logits), len(logits),
+                                 float(scale), _stream(logits[0])),
+              'usl_head_fwd')
+        ctx.scale = float(scale)
+        ctx.save_for_backward(*preds)
+        return tuple(preds)
+
+    @staticmethod
+    def backward(ctx, *grads: Tensor):
+        preds = ctx.saved_tensors
+        gin = [torch.zeros_like(p) if g is None else g.contiguous()
+               for g, p in zip(grads, preds)]
+        gout = [torch.empty_like(p) for p in preds]
+        check(lib().usl_head_bwd(_ptr_array(gin), _ptr_array(preds),
+                                 _ptr_array(gout), _count_array(preds),
+                                 len(preds), ctx.scale, _stream(preds[0])),
+              'usl_head_bwd')
+        return (None,) + tuple(gout)
+
+
+def disc_input(images: Sequence[Tensor], preds: Optional[Sequence[Tensor]],
+               recons: Optional[Sequence[Tensor]]) -> List[Tensor]:
+    """[image level ; its reconstruction] along the batch axis for every level,
+    one launch (include/usl.h: usl_disc_input).  `preds` given: the
+    reconstruction half is warped on the fly; else copied from `recons`."""
+    n = len(images)
+    lv = (_lib.UslDiscLevel * n)()
+    outs, keep = [], []
+    for i in range(n):
+        im = planes(images[i])
+        require_cuda_f32(im, f'image level {i}')
+        b, c, h, w = im.shape
+        if c != 6:
+            raise ValueError('image levels must have 6 channels')
+        out = torch.empty(2 * b, 6, h, w, dtype=im.dtype, device=im.device)
+        lv[i].B, lv[i].h, lv[i].w = b, h, w
+        lv[i].images, lv[i].img_bs, lv[i].img_cs = im.data_ptr(), im.stride(0), im.stride(1)
+        if preds is not None:
+            p = planes(preds[i].detach())
+            require_cuda_f32(p, f'prediction level {i}')
+            lv[i].pred, lv[i].pred_bs, lv[i].pred_cs = p.data_ptr(), p.stride(0), p.stride(1)
+            keep.append(p)
+        else:
+            r = planes(recons[i].detach())
+            require_cuda_f32(r, f'reconstruction level {i}')
+            lv[i].recon, lv[i].rec_bs, lv[i].rec_cs = r.data_ptr(), r.stride(0), r.stride(1)
+            keep.append(r)
+        lv[i].out = out.data_ptr()
+        outs.append(out)
+        keep.append(im)
+    check(lib().usl_disc_input(lv, n, _stream(outs[0])), 'usl_disc_input')
+    return outs
