@@ -133,9 +133,13 @@ def smoothness_kinks(a: Tensor) -> Tensor:
     return m
 
 
-def _disp_term_kinks(im: Tensor, p: Tensor, alpha: float) -> Tensor:
+def _disp_term_kinks(im: Tensor, p: Tensor, alpha: float,
+                     image_eps: float = 0.0) -> Tensor:
     """Kinks of the disparity terms of one scale (reprojection, consistency of
-    the disparity, its smoothness): (B,4,h,w), uncertainty channels untouched."""
+    the disparity, its smoothness): (B,4,h,w), uncertainty channels untouched.
+    `image_eps`: how far an fp32 pyramid level is from the fp64 one (levels
+    below the first are interpolated: on white-noise images the fp32 rounding
+    of the interpolation weights moves a pixel by ~1e-6)."""
     b, _, h, w = p.shape
     m = torch.zeros(b, 4, h, w, dtype=torch.bool)
     eps_ix, eps_iy = IX_EPS_PER_W * w, IX_EPS_PER_W * h
@@ -147,8 +151,9 @@ def _disp_term_kinks(im: Tensor, p: Tensor, alpha: float) -> Tensor:
         m[:, v] |= _near_integer(wi['ix'], eps_ix)
         # K2: |I - recon| per channel (weight 1 - alpha)
         if alpha < 1.0:
+            # (the image and the four pixels the reconstruction blends)
             m[:, v] |= ((own_img - wi['out']).abs() <=
-                        _margin(wi, eps_ix, eps_iy)).any(dim=1)
+                        _margin(wi, eps_ix, eps_iy) + 2.0 * image_eps).any(dim=1)
     ma, mb = consistency_kinks(p[:, 0:2], p[:, 0:2])
     m[:, 0:2] |= ma | mb | smoothness_kinks(p[:, 0:2])
     return m
@@ -179,11 +184,13 @@ def dilate3(mp: Tensor) -> Tensor:
 
 
 def kink_masks(pyramid: Sequence[Tensor], preds: Sequence[Tensor],
-               config: dict, errors: Sequence[Tensor]) -> List[Tensor]:
+               config: dict, errors: Sequence[Tensor],
+               image_eps: Sequence[float] = ()) -> List[Tensor]:
     """Boolean (B,4,h,w) per scale: True where the gradient element of
     prediction channel {d_L, d_R, u_L, u_R} may legitimately differ between an
     fp32 and an fp64 evaluation.  All inputs fp64 (the oracle's pyramid, the
-    predictions, its per-scale error maps E of loss.py:126-131)."""
+    predictions, its per-scale error maps E of loss.py:126-131); `image_eps`:
+    per scale, max |fp32 pyramid - fp64 pyramid| (0 where omitted)."""
     import torch.nn.functional as F
     err_cfg = config.get('error_loss_config') or {}
     loss_type = err_cfg.get('loss_type', 'l1')
@@ -192,8 +199,9 @@ def kink_masks(pyramid: Sequence[Tensor], preds: Sequence[Tensor],
     pooling = bool(err_cfg.get('pooling', False))
     alpha = config.get('wssim_alpha', 0.85)
     masks = []
-    for im, p, e in zip(pyramid, preds, errors):
-        m = _disp_term_kinks(im, p, alpha)
+    for i, (im, p, e) in enumerate(zip(pyramid, preds, errors)):
+        m = _disp_term_kinks(im, p, alpha,
+                             image_eps[i] if i < len(image_eps) else 0.0)
         if pooling:
             # loss.py:420-422: the error terms see 3x3 means; a kink at pooled
             # position q touches the 3x3 inputs under it

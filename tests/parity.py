@@ -34,8 +34,12 @@ def oracle_reference(stereo, preds, cfg):
     from oracle import loss_port as P
     ref = P.step_detailed(stereo.double(), [p.double() for p in preds], cfg)
     assert K.clamp_kinks(ref['pyramid'], ref['recons']) == 0
+    # how far an fp32 pyramid (the reference's, ours) is from the fp64 one
+    pyr32 = P.pyramid(stereo.float(), len(preds))
+    image_eps = [float((a.double() - b).abs().max())
+                 for a, b in zip(pyr32, ref['pyramid'])]
     ref['masks'] = K.kink_masks(ref['pyramid'], ref['preds'], cfg,
-                                ref['errors'])
+                                ref['errors'], image_eps)
     # `pooling`: a kink of a 3x3 mean touches the nine inputs under it
     pooled = bool((cfg.get('error_loss_config') or {}).get('pooling'))
     ref['mask_max'] = MASK_MAX * (9 if pooled else 1)

