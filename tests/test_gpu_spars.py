@@ -187,3 +187,54 @@ def test_other_kernel_sizes_bit_exact(dev, k):
     assert np.array_equal(parts['pooled_pred'].cpu().numpy().reshape(2, 2, -1), pu)
     pc = S.curve(err.to(dev), unc.to(dev), kernel_size=k, device=dev)
     assert np.array_equal(pc.cpu().numpy(), SP.curve_canonical(e, u, k))
+
+
+# ----------------------------------------------------- frames over 2 GPUs ----
+def _sharded_worker(rank, world, port, tmp):
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import spars_port as SP
+    from uncertainty_model_b200 import distributed as D
+    from uncertainty_model_b200.train import sparsification as S
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    d = torch.device('cuda', rank)
+    torch.cuda.set_device(d)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=d)
+    try:
+        err, unc = SP.synthetic_maps(6, 56, 72, seed=4)
+        lo, hi = D.shard_bounds(6, rank, world)
+        out = {}
+        for name, a, c in (('oracle', err, err), ('pred', err, unc)):
+            shard = D.sharded_curve(a[lo:hi].to(d), c[lo:hi].to(d), device=d)
+            single = S.curve(a.to(d), c.to(d), device=d)
+            out[name] = (shard.cpu(), single.cpu())
+        torch.save(out, os.path.join(tmp, f'rank{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_curve_over_two_gpus_is_the_single_gpu_curve(dev, tmp_path):
+    """north_star: frames shard over ranks, the 100-entry fp64 curve sums are
+    all-reduced over NCCL; the curve every rank ends up with is bit for bit
+    the single-GPU curve (distributed.sharded_curve)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    import socket
+    import torch.multiprocessing as mp
+    from oracle import spars_port as SP
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    err, unc = SP.synthetic_maps(6, 56, 72, seed=4)
+    want = {'oracle': SP.curve_canonical(err.numpy(), err.numpy()),
+            'pred': SP.curve_canonical(err.numpy(), unc.numpy())}
+    for rank in range(2):
+        got = torch.load(tmp_path / f'rank{rank}.pt')
+        for name in ('oracle', 'pred'):
+            shard, single = got[name]
+            assert torch.equal(shard, single), (rank, name)
+            assert np.array_equal(single.numpy(), want[name]), (rank, name)

@@ -45,6 +45,14 @@ __device__ __forceinline__ unsigned desc_key(float v) {
     return ~u;                                   // ... reversed
 }
 
+// the float a key stands for (desc_key is a bijection on non-NaN floats but for
+// -0.0, which it canonicalises to +0.0 -- as a sum term the same thing)
+__device__ __forceinline__ float key_value(unsigned k) {
+    unsigned u = ~k;
+    u ^= (u >> 31) ? 0x80000000u : 0xFFFFFFFFu;
+    return __uint_as_float(u);
+}
+
 // ---- pool ---------------------------------------------------------------
 // grid (column groups, blocks of PY output rows, maps).  Each thread produces a
 // PX x PY patch of outputs, so a window row is loaded once -- as 128-bit loads
@@ -243,7 +251,9 @@ __device__ __forceinline__ unsigned same_digit_lanes(unsigned d, bool valid) {
 // digit order in shared memory, and copy it out -- consecutive threads then
 // write consecutive words of a digit's run (a scattered 4-byte store per lane
 // costs a whole sector of load/store-unit time each).
-template <bool WITH_IDX>
+// PAYLOAD: 0 = keys only (the oracle curve ranks the pooled map by itself: the
+// value travels inside its key), 1 = values, 2 = values and element indices.
+template <int PAYLOAD>
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 scatter_kernel(const unsigned* __restrict__ keys_in,
                const float* __restrict__ vals_in, const int* __restrict__ idx_in,
@@ -320,7 +330,7 @@ scatter_kernel(const unsigned* __restrict__ keys_in,
         rank[c] = (unsigned short)(whist[warp][d] + rank[c]);
         if (i < n) {
             skeys[rank[c]] = key[c];
-            sdata[rank[c]] = __float_as_uint(vals_in[rbase + i]);
+            if (PAYLOAD) sdata[rank[c]] = __float_as_uint(vals_in[rbase + i]);
         }
     }
     __syncthreads();
@@ -328,9 +338,9 @@ scatter_kernel(const unsigned* __restrict__ keys_in,
         const unsigned k = skeys[j];
         const long long pos = rbase + delta[(k >> shift) & 255u] + j;
         keys_out[pos] = k;
-        vals_out[pos] = __uint_as_float(sdata[j]);
+        if (PAYLOAD) vals_out[pos] = __uint_as_float(sdata[j]);
     }
-    if (WITH_IDX) {
+    if (PAYLOAD == 2) {
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < SORT_ITEMS; ++c) {
@@ -349,15 +359,18 @@ scatter_kernel(const unsigned* __restrict__ keys_in,
 struct Cuts { int v[USL_MAX_STEPS + 1]; };
 
 // canonical fp64 sum of sorted values with rank in [cut_k, cut_{k+1})
+// (KEYS: the sorted values are read back out of the sorted keys)
+template <bool KEYS>
 __global__ void __launch_bounds__(SEG_LANES)
-segment_kernel(const float* __restrict__ vals, int n, const Cuts cuts,
-               int steps, double* __restrict__ seg) {
+segment_kernel(const float* __restrict__ vals, const unsigned* __restrict__ keys, int n,
+               const Cuts cuts, int steps, double* __restrict__ seg) {
     __shared__ double lanes[SEG_LANES];
     const int k = blockIdx.x, row = blockIdx.y;
     const float* v = vals + (long long)row * n;
+    const unsigned* kk = keys + (long long)row * n;
     double a = 0.0;
     for (int i = cuts.v[k] + threadIdx.x; i < cuts.v[k + 1]; i += SEG_LANES)
-        a = __dadd_rn(a, (double)v[i]);
+        a = __dadd_rn(a, (double)(KEYS ? key_value(kk[i]) : v[i]));
     lanes[threadIdx.x] = a;
     __syncthreads();
     for (int s = SEG_LANES / 2; s >= 1; s >>= 1) {
@@ -487,6 +500,11 @@ extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
     const int n = L.n, ntiles = L.ntiles;
 
     unsigned* digit_base = counts + (size_t)rows * RADIX * ntiles;
+    // the oracle curve: the payload of a key is the float it encodes (the one
+    // difference, -0.0 -> +0.0, is no difference to a sum): keys travel alone,
+    // unless a caller wants the pooled values / the permutation as well
+    const bool key_only = predicted == oracle && !with_idx && !pooled_oracle_out &&
+                          !pooled_pred_out;
     {
         const int oh = H - k + 1, ow = W - k + 1;
         if (oh > 65535 || rows > 65535) return USL_ERR_UNSUPPORTED;
@@ -498,7 +516,9 @@ extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
         if (predicted == oracle) {
             // the oracle curve (evaluate.py:155: curve(error, error)) ranks the
             // map by itself: one pooling pass yields payload and keys
-            pool<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], keys[0]);
+            pool<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo,
+                                                     key_only ? nullptr : vals[0], keys[0]);
+            count_launches(1);
             if (pooled_pred_out &&
                 cudaMemcpyAsync(pooled_pred_out, vals[0], (size_t)rows * n * 4,
                                 cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
@@ -507,15 +527,18 @@ extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
             pool<<<pgrid, POOL_THREADS, 0, stream>>>(oracle, H, W, k, vo, vals[0], nullptr);
             pool<<<pgrid, POOL_THREADS, 0, stream>>>(predicted, H, W, k, vp,
                                                      pooled_pred_out, keys[0]);
+            count_launches(2);
         }
     }
     if (pooled_oracle_out)
         if (cudaMemcpyAsync(pooled_oracle_out, vals[0], (size_t)rows * n * 4,
                             cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
             return USL_ERR_CUDA;
-    if (with_idx)
+    if (with_idx) {
         iota_kernel<<<flat_grid((long long)rows * n), 256, 0, stream>>>(
             idx[0], rows, n);
+        count_launches(1);
+    }
     const dim3 grid(ntiles, rows);
     int cur = 0;
     for (int pass = 0; pass < 4; ++pass) {
@@ -525,21 +548,31 @@ extern "C" int usl_spars_curve(const float* oracle, const float* predicted,
         scan_tiles_kernel<<<dim3(RADIX, rows), 256, 0, stream>>>(counts, ntiles, digit_base);
         scan_digits_kernel<<<rows, RADIX, 0, stream>>>(digit_base);
         if (with_idx)
-            scatter_kernel<true><<<grid, SORT_THREADS, 0, stream>>>(
+            scatter_kernel<2><<<grid, SORT_THREADS, 0, stream>>>(
                 keys[cur], vals[cur], idx[cur], keys[cur ^ 1], vals[cur ^ 1],
                 idx[cur ^ 1], counts, digit_base, n, ntiles, shift);
+        else if (key_only)
+            scatter_kernel<0><<<grid, SORT_THREADS, 0, stream>>>(
+                keys[cur], nullptr, nullptr, keys[cur ^ 1], nullptr,
+                nullptr, counts, digit_base, n, ntiles, shift);
         else
-            scatter_kernel<false><<<grid, SORT_THREADS, 0, stream>>>(
+            scatter_kernel<1><<<grid, SORT_THREADS, 0, stream>>>(
                 keys[cur], vals[cur], nullptr, keys[cur ^ 1], vals[cur ^ 1],
                 nullptr, counts, digit_base, n, ntiles, shift);
         cur ^= 1;
+        count_launches(3);
     }
     if (with_idx)
         if (cudaMemcpyAsync(order_out, idx[cur], (size_t)rows * n * 4,
                             cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
             return USL_ERR_CUDA;
-    segment_kernel<<<dim3(steps, rows), SEG_LANES, 0, stream>>>(vals[cur], n, c,
-                                                               steps, seg);
+    if (key_only)
+        segment_kernel<true><<<dim3(steps, rows), SEG_LANES, 0, stream>>>(
+            vals[cur], keys[cur], n, c, steps, seg);
+    else
+        segment_kernel<false><<<dim3(steps, rows), SEG_LANES, 0, stream>>>(
+            vals[cur], keys[cur], n, c, steps, seg);
+    count_launches(2);
     row_norm_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(seg, rows, n, c, steps);
     accumulate_kernel<<<(steps + 127) / 128, 128, 0, stream>>>(seg, rows, steps,
                                                               row_norm_sum);

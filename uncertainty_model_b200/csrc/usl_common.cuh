@@ -19,6 +19,11 @@ inline std::atomic<long long>& launch_counter() {
     return n;
 }
 
+// (launches that are followed by more launches before the next check_launch)
+inline void count_launches(int n) {
+    launch_counter().fetch_add(n, std::memory_order_relaxed);
+}
+
 inline int check_launch() {
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
