@@ -189,6 +189,11 @@ int usl_loss_bwd(const UslLossConfig* cfgs, const UslLossScale* scales,
  * added to grad_disp.  Neither flag = both, in this order. */
 #define USL_GRAD_NO_SCATTER 2
 #define USL_GRAD_ONLY_SCATTER 4
+/* ... or, keeping the transposed warp of every scale but the largest right
+ * behind that scale's fused kernel (where it is hidden): DEFER_SCATTER0 =
+ * everything but the largest scale's transposed warp, ONLY_SCATTER0 = that. */
+#define USL_GRAD_DEFER_SCATTER0 8
+#define USL_GRAD_ONLY_SCATTER0 16
 int usl_loss_grad(const UslLossConfig* cfgs, const UslLossScale* scales,
                   int n_scales, const float* gout_disp, const float* gout_err,
                   float* partials, int flags, void* stream);

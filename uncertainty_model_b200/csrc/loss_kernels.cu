@@ -485,10 +485,12 @@ struct AfterScale {
     const LossParams* P; int n;
     const float* gout_disp; const float* gout_err;
     int skip;
+    int defer0;        // leave the largest scale's scatter to a later call
 };
 static int scatter_after_scale(void* ctx_, int scale, cudaStream_t st) {
     const AfterScale* c = static_cast<const AfterScale*>(ctx_);
     int rc = USL_OK;
+    if (scale == 0 && c->defer0) return rc;
     launch_scatter(c->P, c->n, c->gout_disp, c->gout_err, 1.0f, c->skip, true, st, &rc,
                    1, true, scale);
     return rc;
@@ -507,6 +509,11 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
     const int skip = (flags & USL_GRAD_SKIP_IF_UNIT) ? 1 : 0;
     // column kernels: they store the gradient, then the scatter adds its part
     // (the read-modify-write sits in the kernel that has warps to spare)
+    if (flags & USL_GRAD_ONLY_SCATTER0) {
+        launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
+                       (cudaStream_t)stream, &rc, 1, true, 0);
+        return rc;
+    }
     if (!(flags & (USL_GRAD_ONLY_SCATTER | USL_GRAD_NO_SCATTER)) && !knobs().exp[1]) {
         // both halves: the scatter of every scale right behind its own fused
         // kernel, on that scale's stream -- the small scales' finish in the
@@ -515,7 +522,8 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
         for (int i = 0; i < n_scales; ++i)
             rows_ok = rows_ok && (!(P[i].terms & (TERM_CONS_D | TERM_CONS_U)) || P[i].scat);
         if (rows_ok) {
-            AfterScale ctx = {P, n_scales, gout_disp, gout_err, skip};
+            AfterScale ctx = {P, n_scales, gout_disp, gout_err, skip,
+                              (flags & USL_GRAD_DEFER_SCATTER0) ? 1 : 0};
             if (!try_col(cfgs, scales, n_scales, true, partials, gout_disp,
                          gout_err, 0, skip, (cudaStream_t)stream, &rc,
                          scatter_after_scale, &ctx))
@@ -528,6 +536,12 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
                      gout_err, 0, skip, (cudaStream_t)stream, &rc))
             return USL_ERR_UNSUPPORTED;
         if (rc != USL_OK) return rc;
+    }
+    if (flags & USL_GRAD_DEFER_SCATTER0) {
+        for (int i = 1; i < n_scales && rc == USL_OK; ++i)
+            launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
+                           (cudaStream_t)stream, &rc, 1, true, i);
+        return rc;
     }
     if (!(flags & USL_GRAD_NO_SCATTER))
         launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,

@@ -168,6 +168,7 @@ def _array(cls, items):
 # --------------------------------------------------------------------------
 MODE_FWD, MODE_GRAD = 0, 1
 GRAD_SKIP_IF_UNIT, GRAD_NO_SCATTER, GRAD_ONLY_SCATTER = 1, 2, 4
+GRAD_DEFER_SCATTER0, GRAD_ONLY_SCATTER0 = 8, 16
 
 
 def plan_rows(cfg_arr, sc_arr, n: int, mode: int) -> Optional[List[int]]:
@@ -226,12 +227,13 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
                        device)
     stream = _stream(partials)
     # sharded batch + gradients: the all-reduce of the sums only needs the fused
-    # kernels, so it runs (NCCL stream) while the scatter kernel works
+    # kernels, so it runs (NCCL stream) while the largest scale's scatter
+    # kernel works (the other scales' ran behind their own fused kernels)
     split = with_grad and reduce_group is not None
     if with_grad:
         check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None,
                               partials.data_ptr(),
-                              GRAD_NO_SCATTER if split else 0, stream),
+                              GRAD_DEFER_SCATTER0 if split else 0, stream),
               'usl_loss_grad')
     else:
         check(L.usl_loss_fwd(cfg_arr, sc_arr, n, partials.data_ptr(), stream),
@@ -242,7 +244,7 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
         work = torch.distributed.all_reduce(sums, group=reduce_group,
                                             async_op=True)
         check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None, None,
-                              GRAD_ONLY_SCATTER, stream), 'usl_loss_grad')
+                              GRAD_ONLY_SCATTER0, stream), 'usl_loss_grad')
         work.wait()
     elif reduce_group is not None:
         torch.distributed.all_reduce(sums, group=reduce_group)
