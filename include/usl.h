@@ -235,6 +235,18 @@ typedef struct UslDiscLevel {
 } UslDiscLevel;
 int usl_disc_input(const UslDiscLevel* levels, int n_levels, void* stream);
 
+/* A gradient arriving at the reconstructions of every level (from the
+ * discriminator, train/loss.py:552-558) -> the disparity channels 0/1 of the
+ * prediction gradients, stored or added (`accumulate`): the transpose of the
+ * warp of utils.py:65-135 w.r.t. its shift, one launch for all levels.
+ * levels[i].images / pred as above (out, recon unused); grad_recon[i]
+ * contiguous (B,6,h,w); grad_pred[i] with batch / channel strides gp_bs[i],
+ * gp_cs[i].  HOST arrays. */
+int usl_recon_bwd(const UslDiscLevel* levels, const float* const* grad_recon,
+                  float* const* grad_pred, const long long* gp_bs,
+                  const long long* gp_cs, int n_levels, int accumulate,
+                  void* stream);
+
 /* ---- train/utils.py:199-245  combine_disparity ----------------------------
  * left, right: contiguous fp32 (planes,h,w); out fp64 like the numpy original. */
 int usl_combine_disparity(const float* left, const float* right, int planes,

@@ -102,6 +102,10 @@ SIGNATURES = {
                                C.c_int, C.c_float, C.c_void_p]),
     'usl_disc_input': (C.c_int, [C.POINTER(UslDiscLevel), C.c_int,
                                  C.c_void_p]),
+    'usl_recon_bwd': (C.c_int, [C.POINTER(UslDiscLevel), C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
+                                C.POINTER(C.c_longlong), C.c_int, C.c_int,
+                                C.c_void_p]),
     'usl_combine_disparity': (C.c_int, [_f32p, _f32p, C.c_int, C.c_int,
                                         C.c_int, C.c_double, C.c_double,
                                         C.c_void_p, C.c_void_p]),

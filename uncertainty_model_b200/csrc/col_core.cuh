@@ -212,8 +212,9 @@ struct alignas(16) RowV {    // vertical taps of the warp for row r + 1
     float w0, w1;            // weights (zero for rows outside the image)
 };
 struct alignas(16) RowW {    // ring synchronisation of the step
-    unsigned wait_cur;       // wait word (c_wait_word) of row r             (0: none)
-    unsigned wait_v0, wait_v1;   // ... of the two source rows of V(r + 1)   (0: none)
+    unsigned wait_cur;       // (unused: the blend touches every row first)
+    unsigned wait_v0, wait_v1;   // wait words (c_wait_word) of the source rows of
+                             // V(r + 1) that no earlier step waited for (0: none)
     int issue;               // row to request at the start of the step (-1: none)
 };
 
@@ -415,12 +416,25 @@ USL_HD void c_init_unit(const LossParams& P, const CGeo& G, const CRings& S,
             const int per_slot = (G.nv == 2 ? NPL : NPO) * SROW;
             v.o0 = c_ring_slot(G, i0) * per_slot;
             v.o1 = c_ring_slot(G, i1) * per_slot;
-            ww.wait_v0 = c_wait_word(S, c_ring_slot(G, i0), c_ring_parity(G, i0));
-            ww.wait_v1 = c_wait_word(S, c_ring_slot(G, i1), c_ring_parity(G, i1));
+            // A row is waited for where a thread first touches it, and never
+            // again (an mbarrier wait costs ~90 cycles even when the row is
+            // there): rows are touched in increasing order, the blend V(r + 1)
+            // touches row r + 1 a phase before P1(r + 1) does, so it is only
+            // the rows V(r + 1) uses that V(r) -- entry i - 1 -- did not.
+            int p0 = -1, p1 = -1;
+            if (i >= 1 && rn - 1 >= 0) {
+                const Tap2 tp = warp_row_taps(rn - 1, P.h);
+                const bool pk0 = tp.i0 >= 0 && tp.i0 < P.h;
+                const bool pk1 = tp.i0 + 1 >= 0 && tp.i0 + 1 < P.h;
+                p0 = pk0 ? tp.i0 : tp.i0 + 1;
+                p1 = pk1 ? tp.i0 + 1 : tp.i0;
+            }
+            if (i0 != p0 && i0 != p1)
+                ww.wait_v0 = c_wait_word(S, c_ring_slot(G, i0), c_ring_parity(G, i0));
+            if (i1 != i0 && i1 != p0 && i1 != p1)
+                ww.wait_v1 = c_wait_word(S, c_ring_slot(G, i1), c_ring_parity(G, i1));
         }
         S.RV[i] = v;
-        if (r >= 0 && r < P.h)
-            ww.wait_cur = c_wait_word(S, c_ring_slot(G, r), c_ring_parity(G, r));
         if (r + 2 >= G.ya && r + 2 <= last) ww.issue = r + 2;
         S.RW[i] = ww;
     }
@@ -562,8 +576,8 @@ USL_HD void c_pV(const LossParams& P, const CGeo& G, const CRings& S, int r,
     if (MODE != MODE_TILED) {
         if (MODE == MODE_PLAIN) {
             const RowW ww = S.RW[i];
-            c_ring_wait<STEADY>(ww.wait_v0);
-            c_ring_wait<STEADY>(ww.wait_v1);
+            c_ring_wait<false>(ww.wait_v0);
+            c_ring_wait<false>(ww.wait_v1);
         }
         if (MODE == MODE_MASKED && !T.active) return;
         const float* a = T.ob + t.o0;
@@ -644,7 +658,6 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
     T.dp = T.d; T.up = T.u;
     if (!STEADY && (r < 0 || r >= P.h)) return;
     const int i = c_step_index(G, r);
-    if (C::MODE == MODE_PLAIN) c_ring_wait<STEADY>(S.RW[i].wait_cur);
     if (MASKED && !T.active) return;
     const RowU ru = S.RU[i];
     const int nh = GRAD ? NHIST_GRAD : NHIST_FWD;
@@ -693,7 +706,9 @@ USL_HD void c_p1(const LossParams& P, const CGeo& G, const CRings& S, int r,
     }
     hs[(nh - 2) * SROW] = l1;
     hs[(nh - 1) * SROW] = T.u;
-    if (!GRAD && C::TERMS < 0 && P.recon_out && own_row && own != 0.f) {
+    // (optional output, generic variant only: the adversarial step hands the
+    //  reconstructions to a discriminator)
+    if (C::TERMS < 0 && P.recon_out && own_row && own != 0.f) {
         const long long hwp = (long long)P.h * P.w;
         for (int c = 0; c < 3; ++c)
             P.recon_out[((long long)G.b * 6 + T.v * 3 + c) * hwp +

@@ -142,6 +142,60 @@ __global__ void __launch_bounds__(GL_THREADS) disc_input_kernel(const __grid_con
     }
 }
 
+// ---- gradient arriving at the reconstructions -> disparities ---------------------
+// grad_d_v[b,y,x] (+)= sign_v * w * sum_c g[b, 3v+c, y, x] *
+//                      [(v01 - v00) * wy0 + (v11 - v10) * wy1]   (utils.py:65-135:
+// the transpose of the warp w.r.t. its shift; a gather with the warp's own taps).
+// a = images, b = prediction (channels 0/1 = d_L, d_R), out = gradient of the
+// prediction (same strides as b: b_bs / b_cs), g in `extra`.
+struct ReconBwd {
+    Levels L;
+    const float* g[USL_MAX_SCALES];     // contiguous (B,6,h,w)
+    long long o_bs[USL_MAX_SCALES], o_cs[USL_MAX_SCALES];
+    int accumulate;
+};
+__global__ void __launch_bounds__(GL_THREADS) recon_bwd_kernel(const __grid_constant__ ReconBwd A) {
+    const Levels& L = A.L;
+    const int s = find_level(L, blockIdx.x);
+    const int h = L.h[s], w = L.w[s];
+    const long long hw = (long long)h * w;
+    const long long n = L.n[s];
+    const int nc = L.cta_start[s + 1] - L.cta_start[s];
+    const long long stride = (long long)nc * GL_THREADS;
+    const float fw = (float)w;
+    for (long long i = (long long)(blockIdx.x - L.cta_start[s]) * GL_THREADS + threadIdx.x;
+         i < n; i += stride) {
+        const int x = (int)(i % w);
+        const int y = (int)((i / w) % h);
+        const int b = (int)(i / hw);
+        const long long pix = (long long)y * w + x;
+        const Tap2 ty = warp_row_taps(y, h);
+        const float* img0 = L.a[s] + b * L.a_bs[s];
+#pragma unroll
+        for (int view = 0; view < 2; ++view) {
+            const float d = __ldg(L.b[s] + b * L.b_bs[s] + view * L.b_cs[s] + pix);
+            const float sign = view ? 1.0f : -1.0f;
+            const Tap2 tx = split_coord(warp_coord(x, w, sign * d));
+            float acc = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* pl = img0 + ((1 - view) * 3 + c) * L.a_cs[s];
+                auto tap = [&](int yy, int xx) {
+                    return (yy >= 0 && yy < h && xx >= 0 && xx < w)
+                               ? __ldg(pl + (long long)yy * w + xx) : 0.0f;
+                };
+                const float v00 = tap(ty.i0, tx.i0), v01 = tap(ty.i0, tx.i0 + 1);
+                const float v10 = tap(ty.i0 + 1, tx.i0), v11 = tap(ty.i0 + 1, tx.i0 + 1);
+                const float go = __ldg(A.g[s] + ((long long)b * 6 + view * 3 + c) * hw + pix);
+                acc += go * ((v01 - v00) * ty.w0 + (v11 - v10) * ty.w1);
+            }
+            float* o = L.out[s] + b * A.o_bs[s] + view * A.o_cs[s] + pix;
+            const float gd = acc * fw * sign;
+            *o = A.accumulate ? *o + gd : gd;
+        }
+    }
+}
+
 // ---- n4 -----------------------------------------------------------------------
 // utils.py:199-245 in the numpy original's fp64: x = linspace(0,1,W)[j];
 // l = 1 - clip(alpha (x - beta), 0, 1); r = l mirrored; out = r * left +
@@ -255,6 +309,34 @@ extern "C" int usl_disc_input(const UslDiscLevel* lv, int levels, void* stream) 
     const int grid = plan_ctas(&L, GL_THREADS * 4);
     if (warp) disc_input_kernel<true><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(L);
     else disc_input_kernel<false><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(L);
+    return check_launch();
+}
+
+extern "C" int usl_recon_bwd(const UslDiscLevel* lv, const float* const* grad_recon,
+                             float* const* grad_pred, const long long* gp_bs,
+                             const long long* gp_cs, int levels, int accumulate,
+                             void* stream) {
+    if (!lv || !grad_recon || !grad_pred || !gp_bs || !gp_cs || levels < 1 ||
+        levels > USL_MAX_SCALES)
+        return USL_ERR_ARG;
+    ReconBwd A = {};
+    A.L.levels = levels;
+    A.accumulate = accumulate;
+    for (int i = 0; i < levels; ++i) {
+        const UslDiscLevel& v = lv[i];
+        if (!v.images || !v.pred || !grad_recon[i] || !grad_pred[i] || v.B < 1 ||
+            v.h < 1 || v.w < 1)
+            return USL_ERR_ARG;
+        A.L.a[i] = v.images; A.L.a_bs[i] = v.img_bs; A.L.a_cs[i] = v.img_cs;
+        A.L.b[i] = v.pred; A.L.b_bs[i] = v.pred_bs; A.L.b_cs[i] = v.pred_cs;
+        A.L.out[i] = grad_pred[i]; A.o_bs[i] = gp_bs[i]; A.o_cs[i] = gp_cs[i];
+        A.g[i] = grad_recon[i];
+        A.L.B[i] = v.B; A.L.h[i] = v.h; A.L.w[i] = v.w;
+        A.L.n[i] = (long long)v.B * v.h * v.w;
+    }
+    DeviceGuard guard(lv[0].images);
+    const int grid = plan_ctas(&A.L, GL_THREADS * 4);
+    recon_bwd_kernel<<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(A);
     return check_launch();
 }
 

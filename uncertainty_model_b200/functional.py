@@ -468,6 +468,8 @@ class ScaleSpec:
     recon: int = -1         # given reconstruction (B,6,h,w)
     err: int = -1           # given error map (B,2,h,w)
     want_err: bool = False  # also return the (B,2,h,w) error map
+    want_recon: bool = False  # also return the (B,6,h,w) reconstruction, as a
+                              # differentiable output (adversarial step)
     flags: int = 0          # USL_SCALE_* (e.g. keep to the general kernels)
 
 
@@ -475,9 +477,14 @@ def _pair(t: Tensor, ch: int) -> ChannelPair:
     return ChannelPair(t, ch)
 
 
+class ReconOutputUnavailable(_lib.UslError):
+    """The fused kernels cannot write the reconstructions for this call."""
+
+
 class FusedLoss(torch.autograd.Function):
     """forward(settings, specs, reduce, *tensors) ->
-           (disp_loss, error_loss, sums[n,6], error maps that were asked for...)
+           (disp_loss, error_loss, sums[n,6], error maps that were asked for...,
+            reconstructions that were asked for...)
 
     Gradients are produced for the disparity / uncertainty tensors and for
     given reconstructions; images and given error maps are data
@@ -505,7 +512,7 @@ class FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def _build(settings, specs, tensors, device, grads=None, errs=None,
-               keep=None):
+               keep=None, recons=None):
         """`keep`: list that receives the workspaces the launch description
         points to (they must outlive it)."""
         cfgs, scales = [], []
@@ -524,6 +531,11 @@ class FusedLoss(torch.autograd.Function):
                 err_out = torch.empty(b, 2, h, w, dtype=torch.float32,
                                       device=device)
                 errs.append(err_out)
+            recon_out = None
+            if recons is not None and sp.want_recon:
+                recon_out = torch.empty(b, 6, h, w, dtype=torch.float32,
+                                        device=device)
+                recons.append(recon_out)
             g = grads if grads is not None else [None] * len(tensors)
             cfgs.append(make_config(sp.terms, settings, sp.coefs))
             scales.append(make_scale(
@@ -533,7 +545,7 @@ class FusedLoss(torch.autograd.Function):
                 shape=(b, h, w),
                 recon_in=tensors[sp.recon] if sp.recon >= 0 else None,
                 err_in=tensors[sp.err] if sp.err >= 0 else None,
-                err_out=err_out,
+                err_out=err_out, recon_out=recon_out,
                 grad_disp=_pair(g[sp.disp], sp.disp_ch)
                 if sp.disp >= 0 and g[sp.disp] is not None else None,
                 grad_unc=_pair(g[sp.unc], sp.unc_ch)
@@ -552,13 +564,15 @@ class FusedLoss(torch.autograd.Function):
         ctx.settings, ctx.specs = settings, specs
         ctx.onepass = None
         errs: List[Tensor] = []
+        recons: List[Tensor] = []
+        ctx.n_recon = 0
         if any(ctx.needs_input_grad[3:]):
             # one pass: the sums and (for unit upstream gradients) the
             # gradients together -- see usl_loss_grad in include/usl.h
             grads = FusedLoss._grad_buffers(specs, tensors)
             keep: List[Tensor] = []
             cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
-                                            grads, errs, keep)
+                                            grads, errs, keep, recons)
             n = len(scales)
             arrays = (_array(UslLossConfig, cfgs), _array(UslLossScale, scales))
             starts = plan_rows(arrays[0], arrays[1], n, MODE_GRAD)
@@ -575,12 +589,17 @@ class FusedLoss(torch.autograd.Function):
                 # backward must not write them again
                 for i in range(n):
                     arrays[1][i].err_out = None
+                    arrays[1][i].recon_out = None
                 ctx.arrays = arrays
                 ctx.save_for_backward(*tensors)
                 ctx.mark_non_differentiable(sums, *errs)
                 ctx.set_materialize_grads(False)
-                return (out_disp, out_err, sums) + tuple(errs)
+                ctx.n_recon = len(recons)
+                return (out_disp, out_err, sums) + tuple(errs) + tuple(recons)
             errs = []
+            if any(sp.want_recon for sp in specs):
+                raise ReconOutputUnavailable(
+                    'reconstruction outputs need the one-pass launch')
         cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
                                         None, errs)
         out_disp, out_err, sums = loss_forward(cfgs, scales, device, reduce)
@@ -588,6 +607,40 @@ class FusedLoss(torch.autograd.Function):
         ctx.mark_non_differentiable(sums, *errs)
         ctx.set_materialize_grads(False)
         return (out_disp, out_err, sums) + tuple(errs)
+
+    @staticmethod
+    def _recon_backward(ctx, specs, tensors, grads, g_recons, device):
+        """A gradient arriving at the reconstruction outputs (from a
+        discriminator) -> added to the disparity gradients, one launch."""
+        levels, gptr, optr, obs, ocs, keep = [], [], [], [], [], []
+        k = 0
+        for sp in specs:
+            if not sp.want_recon:
+                continue
+            g = g_recons[k]
+            k += 1
+            if g is None:
+                continue
+            g = g.contiguous()
+            im, pr, gp = tensors[sp.images], tensors[sp.disp], grads[sp.disp]
+            lv = _lib.UslDiscLevel()
+            lv.B, lv.h, lv.w = im.size(0), im.size(2), im.size(3)
+            lv.images, lv.img_bs, lv.img_cs = im.data_ptr(), im.stride(0), im.stride(1)
+            lv.pred = pr.data_ptr() + 4 * sp.disp_ch * pr.stride(1)
+            lv.pred_bs, lv.pred_cs = pr.stride(0), pr.stride(1)
+            levels.append(lv)
+            gptr.append(g.data_ptr())
+            optr.append(gp.data_ptr() + 4 * sp.disp_ch * gp.stride(1))
+            obs.append(gp.stride(0)); ocs.append(gp.stride(1))
+            keep.append(g)
+        if not levels:
+            return
+        n = len(levels)
+        check(lib().usl_recon_bwd(
+            _array(_lib.UslDiscLevel, levels), (C.c_void_p * n)(*gptr),
+            (C.c_void_p * n)(*optr), (C.c_longlong * n)(*obs),
+            (C.c_longlong * n)(*ocs), n, 1,
+            torch.cuda.current_stream(device).cuda_stream), 'usl_recon_bwd')
 
     @staticmethod
     def backward(ctx, g_disp, g_err, *unused):
@@ -631,6 +684,10 @@ class FusedLoss(torch.autograd.Function):
                 arrays = (_array(UslLossConfig, cfgs),
                           _array(UslLossScale, scales))
                 loss_regrad(arrays, len(specs), gd, ge, device, False)
+            if ctx.n_recon:
+                FusedLoss._recon_backward(ctx, specs, tensors, grads,
+                                          unused[len(unused) - ctx.n_recon:],
+                                          device)
             return (None, None, None) + tuple(
                 g if need else None for g, need in zip(grads, needs))
         grads = FusedLoss._grad_buffers(specs, tensors)

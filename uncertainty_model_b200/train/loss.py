@@ -280,9 +280,17 @@ class TukraUncertaintyLoss(nn.Module):
         preds = list(predictions)[:n_scales]
 
         fused = isinstance(recon_pyramid, ReconPyramid) \
-            and not recon_pyramid.materialised and discriminator is None \
+            and not recon_pyramid.materialised \
             and recon_pyramid.built_from(list(predictions),
                                          list(image_pyramid))
+        # adversarial step on a still-lazy pyramid: the fused kernels warp
+        # in-kernel as always and write the reconstructions out as well (a
+        # differentiable output the discriminator terms consume)
+        emit_recon = fused and discriminator is not None \
+            and not self.predictive_error.pooling \
+            and all(t.requires_grad for t in preds)
+        if fused and discriminator is not None and not emit_recon:
+            fused = False
         recons: Optional[List[Tensor]] = None
         if not fused:
             recons = list(recon_pyramid)[:n_scales]
@@ -302,7 +310,7 @@ class TukraUncertaintyLoss(nn.Module):
             sp = ScaleSpec(terms=disp_terms if pooling
                            else disp_terms | err_terms,
                            coefs=tuple(coefs), want_err=pooling,
-                           flags=self.kernel_flags)
+                           want_recon=emit_recon, flags=self.kernel_flags)
             sp.images = len(tensors); tensors.append(images[i])
             sp.disp = sp.unc = len(tensors); tensors.append(preds[i])
             sp.disp_ch, sp.unc_ch = 0, 2
@@ -314,9 +322,20 @@ class TukraUncertaintyLoss(nn.Module):
         if self.reduce_group is not None:
             reduce = K.Reduce(self.reduce_group,
                               self.grad_world_size / self.world_size)
-        out = FusedLoss.apply(st, specs, reduce, *tensors)
+        try:
+            out = FusedLoss.apply(st, specs, reduce, *tensors)
+        except K.ReconOutputUnavailable:
+            # (shapes the one-pass kernels do not take: materialise the
+            #  pyramid with the stand-alone warp and honour it as given)
+            recon_pyramid.tensors()
+            return self.forward(image_pyramid, predictions, recon_pyramid,
+                                epoch, discriminator)
         disp_loss, error_loss, sums = out[0], out[1], out[2]
         self.last_term_sums = sums
+        if emit_recon:
+            recons = list(out[3:3 + n_scales])
+            # whoever looks at the pyramid next (run_discriminator) finds it
+            recon_pyramid.adopt(recons)
 
         if pooling:
             # loss.py:420-422: the error terms run on 3x3-pooled copies

@@ -88,6 +88,13 @@ class ReconPyramid(Sequence):
                             for d, im in zip(self.disparities, self.pyramid)]
         return self._levels
 
+    def adopt(self, levels: Sequence[Tensor]) -> None:
+        """The levels, computed elsewhere (the fused loss kernels write them
+        out in the adversarial step)."""
+        if len(levels) != len(self.disparities):
+            raise ValueError('one reconstruction per level')
+        self._levels = list(levels)
+
     def built_from(self, disparities: Sequence[Tensor],
                    pyramid: Sequence[Tensor]) -> bool:
         return len(disparities) == len(self.disparities) and \
