@@ -247,6 +247,18 @@ int usl_recon_bwd(const UslDiscLevel* levels, const float* const* grad_recon,
                   const long long* gp_cs, int n_levels, int accumulate,
                   void* stream);
 
+/* ---- train/evaluate.py:142-146  torchmetrics SSIM ---------------------------
+ * structural_similarity_index_measure(preds, target, gaussian_kernel=True,
+ * sigma, kernel_size=k, data_range, k1, k2): per-image values -> per_image[B]
+ * (device fp32; reduction='sum' is their sum).  (B,C,H,W) with contiguous
+ * planes; k odd, <= 15.  See csrc/ssim.cu for the restated algorithm. */
+size_t usl_ssim_workspace_bytes(int B, int C, int H, int W, int k);
+int usl_ssim_gauss(const float* pred, long long p_bs, long long p_cs,
+                   const float* target, long long t_bs, long long t_cs, int B,
+                   int C, int H, int W, int k, float sigma, float data_range,
+                   float k1, float k2, float* per_image, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* ---- train/utils.py:199-245  combine_disparity ----------------------------
  * left, right: contiguous fp32 (planes,h,w); out fp64 like the numpy original. */
 int usl_combine_disparity(const float* left, const float* right, int planes,

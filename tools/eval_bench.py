@@ -48,6 +48,15 @@ def flow(left, right, prediction, dev, ssim_loss, stages=None):
     return out
 
 
+def fused_flow(left, right, prediction, dev):
+    """The same lines as one call (uncertainty_model_b200.train.evaluate):
+    reconstructions + error map from one launch of the column kernels, plus the
+    Gaussian SSIM metric evaluate.py:142-146 asks torchmetrics for."""
+    from uncertainty_model_b200.train import evaluate as E
+    out = E.evaluate_batch(left, right, prediction, device=dev)
+    return out['ause'], out['aurg'], out['left_ssim'], out['right_ssim']
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--frames', type=int, default=8)
@@ -82,6 +91,21 @@ def main():
            'frames_per_s': round(args.frames / (ms * 1e-3), 1),
            'stage_ms': {k: round(v / args.reps, 3) for k, v in acc.items()},
            'ause': float(a[0]), 'aurg': float(a[1])}
+    # ---- fused front half (+ the SSIM metric) --------------------------------
+    for _ in range(2):
+        fa = fused_flow(gl, gr, gp, dev)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(args.reps):
+        fa = fused_flow(gl, gr, gp, dev)
+    t1.record()
+    t1.synchronize()
+    fms = t0.elapsed_time(t1) / args.reps
+    out['fused'] = {'ms': round(fms, 3),
+                    'frames_per_s': round(args.frames / (fms * 1e-3), 1),
+                    'includes': 'SSIM metric of both views',
+                    'ause': float(fa[0]), 'left_ssim': float(fa[2]),
+                    'right_ssim': float(fa[3])}
     if args.cpu_frames > 0:
         from oracle import loss_port as P
         from oracle import spars_port as SP

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libusl.so')
-SOURCES = ['pyramid.cu', 'warp.cu', 'misc.cu', 'glue.cu', 'loss_kernels.cu',
+SOURCES = ['pyramid.cu', 'warp.cu', 'misc.cu', 'glue.cu', 'ssim.cu', 'loss_kernels.cu',
            'col_kernels.cu', 'col_inst_512.cu', 'col_inst_256.cu',
            'col_inst_128.cu', 'col_inst_64.cu', 'cons_kernels.cu', 'cons_rows.cu',
            'spars.cu']

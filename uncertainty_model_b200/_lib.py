@@ -106,6 +106,13 @@ SIGNATURES = {
                                 C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
                                 C.POINTER(C.c_longlong), C.c_int, C.c_int,
                                 C.c_void_p]),
+    'usl_ssim_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_int]),
+    'usl_ssim_gauss': (C.c_int, [_f32p, C.c_longlong, C.c_longlong, _f32p,
+                                 C.c_longlong, C.c_longlong, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_float,
+                                 C.c_float, C.c_float, C.c_float, _f32p,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     'usl_combine_disparity': (C.c_int, [_f32p, _f32p, C.c_int, C.c_int,
                                         C.c_int, C.c_double, C.c_double,
                                         C.c_void_p, C.c_void_p]),

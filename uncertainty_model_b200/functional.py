@@ -600,13 +600,15 @@ class FusedLoss(torch.autograd.Function):
             if any(sp.want_recon for sp in specs):
                 raise ReconOutputUnavailable(
                     'reconstruction outputs need the one-pass launch')
+        # forward only (no gradient asked for): sums, and the optional maps
+        recons = []
         cfgs, scales = FusedLoss._build(settings, specs, tensors, device,
-                                        None, errs)
+                                        None, errs, recons=recons)
         out_disp, out_err, sums = loss_forward(cfgs, scales, device, reduce)
         ctx.save_for_backward(*tensors)
-        ctx.mark_non_differentiable(sums, *errs)
+        ctx.mark_non_differentiable(sums, *errs, *recons)
         ctx.set_materialize_grads(False)
-        return (out_disp, out_err, sums) + tuple(errs)
+        return (out_disp, out_err, sums) + tuple(errs) + tuple(recons)
 
     @staticmethod
     def _recon_backward(ctx, specs, tensors, grads, g_recons, device):
