@@ -27,7 +27,9 @@ def scale_pyramid(x: Tensor, scales: int) -> ImagePyramid:
     from the full-resolution input (reference utils.py:27-50).
 
     Level 0 is `x` itself, not a copy: the reference's level 0 is a
-    bit-identical resample.  One kernel launch produces all other levels."""
+    bit-identical resample.  Nothing on the path writes into a level; a caller
+    who mutates level 0 in place mutates `x` (clone it first if that matters).
+    One kernel launch produces all other levels."""
     return K.pyramid(x, scales)
 
 
