@@ -198,6 +198,22 @@ int usl_loss_grad(const UslLossConfig* cfgs, const UslLossScale* scales,
                   int n_scales, const float* gout_disp, const float* gout_err,
                   float* partials, int flags, void* stream);
 
+/* Batch sharded over ranks (reference parallel_main.py: one process per GPU,
+ * loss.py:560-566 evaluated per rank): usl_loss_grad for unit upstream
+ * gradients, AND usl_loss_reduce(partials, cta_starts, n_scales, sums)
+ * enqueued on `reduce_stream` behind the column kernels only -- not behind the
+ * transposed warps, which need another ~25 % of the step.  The caller enqueues
+ * its exchange of `sums` between ranks behind `reduce_stream` and joins it to
+ * `stream` before usl_loss_combine; the exchange then runs beside the
+ * transposed warp.  reduce_stream: a cudaStream_t of the same device, different
+ * from `stream` (it is made to wait for work forked from `stream`, so it takes
+ * part in a stream capture of `stream`).  USL_ERR_UNSUPPORTED where
+ * usl_loss_grad would not run its per-scale transposed warps (the caller then
+ * uses usl_loss_grad + usl_loss_reduce). */
+int usl_loss_grad_sharded(const UslLossConfig* cfgs, const UslLossScale* scales,
+                          int n_scales, float* partials, const int* cta_starts,
+                          double* sums, void* reduce_stream, void* stream);
+
 /* The gradients usl_loss_grad wrote are those for unit upstream gradients, and
  * they are linear in the upstream pair.  When BOTH outputs receive the SAME
  * upstream gradient g (the training loop back-propagates disp_loss +

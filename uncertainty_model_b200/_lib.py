@@ -80,6 +80,10 @@ SIGNATURES = {
     'usl_loss_grad': (C.c_int, [C.POINTER(UslLossConfig),
                                 C.POINTER(UslLossScale), C.c_int, _f32p, _f32p,
                                 _f32p, C.c_int, C.c_void_p]),
+    'usl_loss_grad_sharded': (C.c_int, [C.POINTER(UslLossConfig),
+                                        C.POINTER(UslLossScale), C.c_int,
+                                        _f32p, C.POINTER(C.c_int), C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     'usl_loss_fwd_ctas': (C.c_int, [C.POINTER(UslLossScale)]),
     'usl_loss_fwd': (C.c_int, [C.POINTER(UslLossConfig),
                                C.POINTER(UslLossScale), C.c_int, _f32p,

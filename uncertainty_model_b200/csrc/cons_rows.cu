@@ -154,10 +154,10 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
     const int nwalk = nl >> 5;                  // walking warps: 0 .. nwalk-1
     const int ntile = (w + R4_TILE - 1) / R4_TILE;
 
-    for (int i = tid; i < nl * HW; i += R4_THREADS) H[i] = 0.0f;
-    // rows past the strip are never copied: their lanes must read zeros
+    // H (nl * HW floats, nl a multiple of 32: whole 16-byte words) and the ring:
+    // rows past the strip are never copied, their lanes must read zeros
     // (contributions 0 into column -2, a pad)
-    for (int i = tid; i < R4_STAGES * nl * R4_PITCH; i += R4_THREADS)
+    for (int i = tid; i < R4_STAGES * nl * R4_PITCH + nl * HW / 4; i += R4_THREADS)
         stage[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     if (tid == 0) {
@@ -334,18 +334,20 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
             const float* h1 = H + ((size_t)row[1] * 2 + (1 - o)) * HW + R4_PAD;
             const float* h2 = H + ((size_t)row[2] * 2 + (1 - o)) * HW + R4_PAD;
             float* out = P.grad_disp + (long long)b * P.gd_bs + o * P.gd_cs + (long long)yd * w;
+            // One add per destination element, by the only thread that owns it in
+            // this launch, onto what an EARLIER launch stored: a reduction
+            // instruction (no return value, the add happens in L2) gives the bits
+            // of load-add-store without a round trip per element.
             for (int x0 = lane; x0 < w; x0 += 256) {
-                float old[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int x = x0 + 32 * u;
-                    old[u] = (P.accumulate && x < w) ? out[x] : 0.0f;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int x = x0 + 32 * u;
-                    if (x < w)
-                        out[x] = old[u] + (wgt[0] * h0[x] + wgt[1] * h1[x] + wgt[2] * h2[x]);
+                    if (x >= w) continue;
+                    const float v = wgt[0] * h0[x] + wgt[1] * h1[x] + wgt[2] * h2[x];
+                    if (P.accumulate)
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(out + x), "f"(v) : "memory");
+                    else
+                        out[x] = v;
                 }
             }
         }

@@ -486,10 +486,18 @@ struct AfterScale {
     const float* gout_disp; const float* gout_err;
     int skip;
     int defer0;        // leave the largest scale's scatter to a later call
+    cudaStream_t reduce_stream;   // if set: made to wait for every column kernel
 };
 static int scatter_after_scale(void* ctx_, int scale, cudaStream_t st) {
     const AfterScale* c = static_cast<const AfterScale*>(ctx_);
     int rc = USL_OK;
+    if (c->reduce_stream) {
+        // the partial sums of this scale are complete here, before its scatter
+        StreamPool* pool = stream_pool();
+        if (!pool || cudaEventRecord(pool->col_done[scale], st) != cudaSuccess ||
+            cudaStreamWaitEvent(c->reduce_stream, pool->col_done[scale], 0) != cudaSuccess)
+            return USL_ERR_CUDA;
+    }
     if (scale == 0 && c->defer0) return rc;
     launch_scatter(c->P, c->n, c->gout_disp, c->gout_err, 1.0f, c->skip, true, st, &rc,
                    1, true, scale);
@@ -523,7 +531,7 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
             rows_ok = rows_ok && (!(P[i].terms & (TERM_CONS_D | TERM_CONS_U)) || P[i].scat);
         if (rows_ok) {
             AfterScale ctx = {P, n_scales, gout_disp, gout_err, skip,
-                              (flags & USL_GRAD_DEFER_SCATTER0) ? 1 : 0};
+                              (flags & USL_GRAD_DEFER_SCATTER0) ? 1 : 0, nullptr};
             if (!try_col(cfgs, scales, n_scales, true, partials, gout_disp,
                          gout_err, 0, skip, (cudaStream_t)stream, &rc,
                          scatter_after_scale, &ctx))
@@ -547,6 +555,36 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
         launch_scatter(P, n_scales, gout_disp, gout_err, 1.0f, skip, true,
                        (cudaStream_t)stream, &rc, 1, true);
     return rc;
+}
+
+extern "C" int usl_loss_grad_sharded(const UslLossConfig* cfgs,
+                                     const UslLossScale* scales, int n_scales,
+                                     float* partials, const int* cta_starts,
+                                     double* sums, void* reduce_stream,
+                                     void* stream) {
+    if (!cfgs || !scales || n_scales < 1 || n_scales > USL_MAX_SCALES ||
+        !partials || !cta_starts || !sums || !reduce_stream || reduce_stream == stream)
+        return USL_ERR_ARG;
+    DeviceGuard guard(any_tensor(scales, n_scales));
+    if (!col_ready(cfgs, scales, n_scales, true)) return USL_ERR_UNSUPPORTED;
+    LossParams P[USL_MAX_SCALES];
+    int rc = fill_all(cfgs, scales, n_scales, false, P);
+    if (rc != USL_OK) return rc;
+    for (int i = 0; i < n_scales; ++i)
+        if ((P[i].terms & (TERM_CONS_D | TERM_CONS_U)) && !P[i].scat)
+            return USL_ERR_UNSUPPORTED;
+    if (knobs().exp[1]) return USL_ERR_UNSUPPORTED;
+    AfterScale ctx = {P, n_scales, nullptr, nullptr, 0, 0, (cudaStream_t)reduce_stream};
+    if (!try_col(cfgs, scales, n_scales, true, partials, nullptr, nullptr, 0, 0,
+                 (cudaStream_t)stream, &rc, scatter_after_scale, &ctx))
+        return USL_ERR_UNSUPPORTED;
+    if (rc != USL_OK) return rc;
+    // (reduce_stream now waits for the four column kernels, not for the scatters)
+    CtaStarts st;
+    for (int i = 0; i <= n_scales; ++i) st.v[i] = cta_starts[i];
+    reduce_partials_kernel<<<n_scales * NUM_ACC, 256, 0, (cudaStream_t)reduce_stream>>>(
+        partials, st, n_scales, sums);
+    return check_launch();
 }
 
 extern "C" int usl_loss_bwd(const UslLossConfig* cfgs,

@@ -126,6 +126,7 @@ struct StreamPool {
     cudaStream_t side[USL_MAX_SCALES];
     cudaStream_t first;
     cudaEvent_t fork, fork2, join[USL_MAX_SCALES], join_first;
+    cudaEvent_t col_done[USL_MAX_SCALES];   // a scale's column kernel (not its scatter) has finished
 };
 inline StreamPool* stream_pool() {
     constexpr int MAX_DEV = 64;
@@ -143,7 +144,8 @@ inline StreamPool* stream_pool() {
                   cudaEventCreateWithFlags(&p.fork2, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < USL_MAX_SCALES; ++i)
             ok = cudaStreamCreateWithFlags(&p.side[i], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) == cudaSuccess;
+                 cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p.col_done[i], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { p.failed = true; cudaGetLastError(); return nullptr; }
         p.ready = true;
     }

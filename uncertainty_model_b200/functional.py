@@ -226,11 +226,27 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
     coef = coef_tensor(tuple(tuple(k * cscale for k in c.coef) for c in cfgs),
                        device)
     stream = _stream(partials)
-    # sharded batch + gradients: the all-reduce of the sums only needs the fused
-    # kernels, so it runs (NCCL stream) while the largest scale's scatter
-    # kernel works (the other scales' ran behind their own fused kernels)
+    # sharded batch + gradients: the all-reduce of the sums only needs the
+    # column kernels, so it runs (side stream -> NCCL stream) beside the
+    # transposed warps
     split = with_grad and reduce_group is not None
-    if with_grad:
+    starts_arr = (C.c_int * (n + 1))(*starts)
+    done = False
+    if split:
+        side = _reduce_stream(partials.device)
+        rc = L.usl_loss_grad_sharded(cfg_arr, sc_arr, n, partials.data_ptr(),
+                                     starts_arr, sums.data_ptr(),
+                                     side.cuda_stream, stream)
+        if rc != _lib.USL_ERR_UNSUPPORTED:
+            check(rc, 'usl_loss_grad_sharded')
+            with torch.cuda.stream(side):
+                work = torch.distributed.all_reduce(sums, group=reduce_group,
+                                                    async_op=True)
+            work.wait()     # the caller's stream waits for the collective
+            done = True
+    if done:
+        pass
+    elif with_grad:
         check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None,
                               partials.data_ptr(),
                               GRAD_DEFER_SCATTER0 if split else 0, stream),
@@ -238,16 +254,17 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
     else:
         check(L.usl_loss_fwd(cfg_arr, sc_arr, n, partials.data_ptr(), stream),
               'usl_loss_fwd')
-    check(L.usl_loss_reduce(partials.data_ptr(), (C.c_int * (n + 1))(*starts),
-                            n, sums.data_ptr(), stream), 'usl_loss_reduce')
-    if split:
-        work = torch.distributed.all_reduce(sums, group=reduce_group,
-                                            async_op=True)
-        check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None, None,
-                              GRAD_ONLY_SCATTER0, stream), 'usl_loss_grad')
-        work.wait()
-    elif reduce_group is not None:
-        torch.distributed.all_reduce(sums, group=reduce_group)
+    if not done:
+        check(L.usl_loss_reduce(partials.data_ptr(), starts_arr, n,
+                                sums.data_ptr(), stream), 'usl_loss_reduce')
+        if split:
+            work = torch.distributed.all_reduce(sums, group=reduce_group,
+                                                async_op=True)
+            check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None, None,
+                                  GRAD_ONLY_SCATTER0, stream), 'usl_loss_grad')
+            work.wait()
+        elif reduce_group is not None:
+            torch.distributed.all_reduce(sums, group=reduce_group)
     check(L.usl_loss_combine(sums.data_ptr(), coef.data_ptr(), n,
                              out_disp.data_ptr(), out_err.data_ptr(), stream),
           'usl_loss_combine')
@@ -255,6 +272,17 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
 
 
 _COEF_CACHE = {}
+_REDUCE_STREAMS = {}
+
+
+def _reduce_stream(device) -> 'torch.cuda.Stream':
+    """Per-device side stream on which the term sums of a sharded batch are
+    reduced and handed to the collective (usl_loss_grad_sharded)."""
+    key = (device.type, device.index)
+    st = _REDUCE_STREAMS.get(key)
+    if st is None:
+        st = _REDUCE_STREAMS[key] = torch.cuda.Stream(device)
+    return st
 
 
 def coef_tensor(coefs, device) -> Tensor:
