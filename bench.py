@@ -704,6 +704,9 @@ def kernel_times(K, hz, dev, reps):
     # in the step every scale's scatter runs right behind its own fused kernel)
     out['loss_fused_main'] = t(lambda i: grad_call(i, K.GRAD_NO_SCATTER))
     out['loss_scatter'] = t(lambda i: grad_call(i, K.GRAD_ONLY_SCATTER))
+    # the largest scale's alone: the one that is on the step's critical path
+    out['loss_scatter_scale0'] = t(
+        lambda i: grad_call(i, K.GRAD_ONLY_SCATTER0))
     # ... and as the step issues them: fused + scatter, per scale, concurrent
     out['loss_fused_plus_scatter'] = t(lambda i: grad_call(i, 0))
     # the training step's loss: that plus reduce + combine

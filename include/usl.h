@@ -52,6 +52,14 @@ int usl_version(void);
 const char* usl_strerror(int rc);
 /* kernel launches this process has issued through the library so far */
 long long usl_launch_count(void);
+/* Profiling aid.  slots: device buffer of USL_TIMELINE_SLOTS uint64 (or NULL to
+ * switch it off).  While set, one-thread marker kernels write %globaltimer
+ * (ns) into it around the launches of a training step: 0/1 before/after the
+ * pyramid kernel, 2+i after scale i's fused kernel, 6+i after its transposed
+ * warp, 10 after the reduction, 11 after the combination, 12 after the
+ * rescale.  Works inside a CUDA-graph replay (tools/step_timeline.py). */
+#define USL_TIMELINE_SLOTS 16
+int usl_debug_timeline(void* slots);
 
 /* ---- train/utils.py:27-50  scale_pyramid ---------------------------------
  * src (B,C,H,W).  dst[i], i = 1..scales-1, contiguous (B,C,H>>i,W>>i);

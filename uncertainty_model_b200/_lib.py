@@ -84,6 +84,7 @@ SIGNATURES = {
                                         C.POINTER(UslLossScale), C.c_int,
                                         _f32p, C.POINTER(C.c_int), C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    'usl_debug_timeline': (C.c_int, [C.c_void_p]),
     'usl_loss_fwd_ctas': (C.c_int, [C.POINTER(UslLossScale)]),
     'usl_loss_fwd': (C.c_int, [C.POINTER(UslLossConfig),
                                C.POINTER(UslLossScale), C.c_int, _f32p,

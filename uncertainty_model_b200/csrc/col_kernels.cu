@@ -149,7 +149,8 @@ int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st,
     if (!pool) {
         for (int i = 0; i < M->n; ++i) {
             int rc = col_launch_scale(M, i, grad, skip_if_unit, st);
-            if (rc == USL_OK && after) rc = after(after_ctx, i, st);
+            mark(2 + i, st);
+            if (rc == USL_OK && after) { rc = after(after_ctx, i, st); mark(6 + i, st); }
             if (rc != USL_OK) return rc;
         }
         return USL_OK;
@@ -164,19 +165,22 @@ int col_launch(const ColPlan* M, bool grad, int skip_if_unit, cudaStream_t st,
     if (hi) {
         if (cudaStreamWaitEvent(pool->first, pool->fork, 0) != cudaSuccess) return USL_ERR_CUDA;
         rc = col_launch_scale(M, 0, grad, skip_if_unit, pool->first);
-        if (rc == USL_OK && after) rc = after(after_ctx, 0, pool->first);
+        mark(2, pool->first);
+        if (rc == USL_OK && after) { rc = after(after_ctx, 0, pool->first); mark(6, pool->first); }
         if (cudaEventRecord(pool->join_first, pool->first) != cudaSuccess ||
             cudaStreamWaitEvent(st, pool->join_first, 0) != cudaSuccess)
             rc = rc == USL_OK ? USL_ERR_CUDA : rc;
     } else {
         rc = col_launch_scale(M, 0, grad, skip_if_unit, st);
-        if (rc == USL_OK && after) rc = after(after_ctx, 0, st);
+        mark(2, st);
+        if (rc == USL_OK && after) { rc = after(after_ctx, 0, st); mark(6, st); }
     }
     for (int i = 1; i < M->n && rc == USL_OK; ++i) {
         cudaStream_t s = pool->side[i - 1];
         if (cudaStreamWaitEvent(s, pool->fork, 0) != cudaSuccess) { rc = USL_ERR_CUDA; break; }
         rc = col_launch_scale(M, i, grad, skip_if_unit, s);
-        if (rc == USL_OK && after) rc = after(after_ctx, i, s);
+        mark(2 + i, s);
+        if (rc == USL_OK && after) { rc = after(after_ctx, i, s); mark(6 + i, s); }
         // join even after a failed launch so that `st` stays well ordered
         if (cudaEventRecord(pool->join[i - 1], s) != cudaSuccess ||
             cudaStreamWaitEvent(st, pool->join[i - 1], 0) != cudaSuccess)

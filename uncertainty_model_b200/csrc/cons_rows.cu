@@ -22,12 +22,14 @@
 // that cannot be recomputed without the blended row).  The warps of the CTA that
 // do not walk turn them, a tile of 16 columns ahead, into what the chain
 // consumes -- the tap contributions s * w0, s * w1 of both terms and the row
-// addresses of their first taps -- and hand them over through a 3-stage ring in
+// addresses of their first taps -- and hand them over through a 4-stage ring in
 // shared memory (mbarriers; a 336-byte block per row and tile, odd in 16-byte
-// units so that the column walk is bank-conflict free).  The walkers interleave
-// the read-modify-writes of 8 columns with the ring loads of the next 8, and
-// run the two terms of a column as ONE chain (loads, forwarding of the first
-// term's sums where the taps coincide, stores in order).
+// units so that the column walk is bank-conflict free).  The records reach the
+// ring by asynchronous 16-byte copies issued three tiles ahead and are decoded
+// in place.  The walkers interleave the read-modify-writes of 8 columns with the
+// ring loads of the next 8, and run the two terms of a column as ONE round trip
+// (four loads, four adds, four stores; where taps of the two terms coincide the
+// later store carries both contributions, summed off the dependent chain).
 //
 // CTA = destination rows [ya, yb) of one sample; lane t = rsi * 2 + v walks
 // source row rs0 + rsi of view v.  At the end all warps assemble the destination
@@ -39,16 +41,17 @@
 
 namespace usl {
 
-constexpr int R4_THREADS = 256;
+constexpr int R4_THREADS = 320;
 constexpr int R4_TILE = 16;                 // columns per staged tile
 constexpr int R4_PITCH = R4_TILE + 4 + 1;   // 16-byte elements per staged (row, tile) block:
                                             // 16 contribution quadruples, 16 column pairs (odd: the
                                             // column walk is bank-conflict free)
-constexpr int R4_STAGES = 3;
+constexpr int R4_STAGES = 4;
 constexpr int R4_PAD = 2;                   // row = [2 | w | 2 (+1)]: taps outside the
                                             // image land in the pads
 constexpr int R4_BATCH = 8;
-constexpr int R4_MAXE = 11;                 // elements of a tile per preparing thread
+constexpr int R4_SMEM_LIMIT = 224 * 1024;    // of the 227 KB a CTA may have
+constexpr int R4_MAXE = 4;                  // elements of a tile per preparing thread
 
 // floats per private row: odd, so that lanes at the same column (smooth
 // disparities) sit in 32 different banks
@@ -56,9 +59,15 @@ __host__ __device__ inline int r4_pitch(int w) { return (w + 2 * R4_PAD) | 1; }
 
 struct R4Geo { int nl, R; size_t smem; };
 
+// ring bytes (reused after the walk as the transposition scratch of the
+// assembly: a 32 x 33 float tile per warp)
+__host__ __device__ inline size_t r4_ring_bytes(int nl) {
+    const size_t ring = (size_t)R4_STAGES * nl * R4_PITCH * 16;
+    const size_t scratch = (size_t)(R4_THREADS / 32) * 32 * 33 * 4;
+    return ring > scratch ? ring : scratch;
+}
 __host__ __device__ inline size_t r4_smem(int nl, int w) {
-    return (size_t)nl * r4_pitch(w) * 4 +
-           (size_t)R4_STAGES * nl * R4_PITCH * 16 + 64;
+    return (size_t)nl * r4_pitch(w) * 4 + r4_ring_bytes(nl) + 64;
 }
 
 // walking lanes (32 .. 128) and strip height of a scale; nl = 0 if even 32
@@ -68,7 +77,7 @@ static R4Geo r4_geometry(int h, int w, size_t budget) {
     for (int nl = 128; nl >= 32; nl -= 32) {
         if (r4_smem(nl, w) > budget) continue;
         // a preparing thread takes at most R4_MAXE of the nl * 16 elements of a tile
-        if (nl * R4_TILE > R4_MAXE * (((R4_THREADS - nl) / 64) * 32)) continue;
+        if (nl * R4_TILE > R4_MAXE * (R4_THREADS - nl)) continue;
         // no point in more rows than the image has
         if (nl > 32 && (nl - 32) / 2 >= h) continue;
         g.nl = nl; g.smem = r4_smem(nl, w);
@@ -147,7 +156,7 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
     const int rs1 = min(yb, h - 1);             // last one
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float4* stage = smem_raw;                                       // [STAGES][nl][PITCH]
-    float* H = reinterpret_cast<float*>(stage + (size_t)R4_STAGES * nl * R4_PITCH);  // [nl][HW]
+    float* H = reinterpret_cast<float*>(reinterpret_cast<char*>(stage) + r4_ring_bytes(nl));  // [nl / 32][HW][32]
     uint64_t* full = reinterpret_cast<uint64_t*>(H + (size_t)nl * HW);  // [STAGES]
     uint64_t* empty = full + R4_STAGES;                                 // [STAGES]
     const long long hw = (long long)h * w;
@@ -157,13 +166,13 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
     // H (nl * HW floats, nl a multiple of 32: whole 16-byte words) and the ring:
     // rows past the strip are never copied, their lanes must read zeros
     // (contributions 0 into column -2, a pad)
-    for (int i = tid; i < R4_STAGES * nl * R4_PITCH + nl * HW / 4; i += R4_THREADS)
+    for (int i = tid; i < (int)(r4_ring_bytes(nl) / 16) + nl * HW / 4; i += R4_THREADS)
         stage[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     if (tid == 0) {
         // (every preparing warp arrives once per tile, every walking warp releases it)
         for (int k = 0; k < R4_STAGES; ++k) {
-            mb_init(full + k, (R4_THREADS / 32 - nwalk) / 2);
+            mb_init(full + k, R4_THREADS / 32 - nwalk);
             mb_init(empty + k, nwalk);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -173,58 +182,97 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
 
     if (warp >= nwalk) {
         // ---- the preparing warps: {d, u, s_dd, s_ud} of a tile (16 columns of
-        // every row) -> tap contributions + tap columns in the ring.  Two groups
-        // of warps take alternate tiles: a thread loads its elements, waits for
-        // them, decodes, stores -- while it waits on memory the other group
-        // works.  (Prefetching the next tile into registers instead does not
-        // overlap anything: the wait for this tile's loads drains the same
-        // scoreboard the new loads were just put on.)  Consecutive threads take
-        // consecutive columns of a row: coalesced 16-byte loads.
-        const int npw = ((R4_THREADS / 32 - nwalk) / 2) * 2;   // warps used: two equal groups
-        const int pw = warp - nwalk;
-        if (pw < npw) {
-            const int g = pw & 1, gt = (pw >> 1) * 32 + lane, gn = (npw / 2) * 32;
-            const int nrows = (rs1 - rs0 + 1) * 2;
-            const int nelem = nrows * R4_TILE;             // per tile
-            const float fw = (float)w, hwf = 0.5f * fw;
-            const float4* src0 = reinterpret_cast<const float4*>(P.scat) + (long long)b * 2 * hw;
-            for (int k = g; k < ntile; k += 2) {
-                const int st = k % R4_STAGES;
-                float4 q[R4_MAXE];
+        // every row) -> tap contributions + tap columns in the ring.  The records
+        // come in by 16-byte asynchronous copies STRAIGHT INTO the ring slots
+        // they are decoded in, R4_STAGES - 1 tiles ahead: no registers or
+        // scoreboard entries are held while they fly, so the memory latency of
+        // three tiles overlaps the decoding of one.  (Two groups of warps on
+        // alternate tiles with plain loads waited two thirds of the time; a
+        // register prefetch of the next tile does not overlap anything -- the
+        // wait for this tile's loads drains the scoreboard the new loads were
+        // just put on.)  A thread decodes what it copied itself: its own
+        // wait_group is all the synchronisation the copies need.  Consecutive
+        // threads take consecutive columns of a row: 256 contiguous bytes.
+        const int npw = R4_THREADS / 32 - nwalk;
+        const int gt = (warp - nwalk) * 32 + lane, gn = npw * 32;
+        const int nelem = (rs1 - rs0 + 1) * 2 * R4_TILE;      // per tile
+        const float fw = (float)w, hwf = 0.5f * fw;
+        const float4* src0 = reinterpret_cast<const float4*>(P.scat) + (long long)b * 2 * hw;
+        // (what a thread has no element for goes to the pad slot of row 0's
+        //  block: straight-line code, the four decodes of a thread interleave)
+        const float step = w > 1 ? 1.0f / (float)(w - 1) : 0.0f;
+        auto issue = [&](int k) {
+            const int st = k % R4_STAGES;
 #pragma unroll
-                for (int i = 0; i < R4_MAXE; ++i) {
-                    const int e = gt + i * gn;
-                    const int t = e / R4_TILE, x = k * R4_TILE + (e % R4_TILE);
-                    q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (e < nelem && x < w)
-                        q[i] = __ldg(src0 + (long long)(t & 1) * hw +
-                                     (long long)(rs0 + (t >> 1)) * w + x);
-                }
-                if (k >= R4_STAGES) mb_wait(empty + st, ((k / R4_STAGES) - 1) & 1);
-#pragma unroll
-                for (int i = 0; i < R4_MAXE; ++i) {
-                    const int e = gt + i * gn;
-                    if (e >= nelem) continue;
-                    const int t = e / R4_TILE, j = e % R4_TILE;
-                    const float sign = (t & 1) ? 1.0f : -1.0f;
-                    const float xb = linspace01(k * R4_TILE + j, w);
-                    unsigned cd, cu;
-                    float4 c;
-                    r4_decode(xb, sign * q[i].x, q[i].z, hwf, fw, cd, c.x, c.y);
-                    r4_decode(xb, sign * q[i].y, q[i].w, hwf, fw, cu, c.z, c.w);
-                    float4* blk = stage + ((size_t)st * nl + t) * R4_PITCH;
-                    blk[j] = c;
-                    reinterpret_cast<unsigned*>(blk + R4_TILE)[j] = cd | (cu << 16);
-                }
-                __syncwarp();
-                if (lane == 0) mb_arrive(full + st);
+            for (int i = 0; i < R4_MAXE; ++i) {
+                const int e = gt + i * gn;
+                const bool have = e < nelem;
+                const int t = have ? e / R4_TILE : 0, j = have ? e % R4_TILE : R4_PITCH - 1;
+                const int x = k * R4_TILE + (e % R4_TILE);
+                const bool in = have && x < w;         // (past the row: zero fill)
+                const float4* src = src0 + (long long)(t & 1) * hw +
+                                    (long long)(rs0 + (t >> 1)) * w + (in ? x : 0);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::
+                             "r"(s_u32(stage + ((size_t)st * nl + t) * R4_PITCH + j)),
+                             "l"(src), "r"(in ? 16 : 0) : "memory");
             }
+        };
+        // (a group is committed per tile slot whether or not it holds copies, so
+        //  that "all but the newest R4_STAGES - 2 groups" always means tile k)
+        for (int k = 0; k < R4_STAGES - 1; ++k) {
+            if (k < ntile) issue(k);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int k = 0; k < ntile; ++k) {
+            const int st = k % R4_STAGES;
+            asm volatile("cp.async.wait_group %0;" ::"n"(R4_STAGES - 2) : "memory");
+#pragma unroll
+            for (int i = 0; i < R4_MAXE; ++i) {
+                const int e = gt + i * gn;
+                const bool have = e < nelem;
+                const int t = have ? e / R4_TILE : 0, j = e % R4_TILE;
+                float4* blk = stage + ((size_t)st * nl + t) * R4_PITCH;
+                const float4 q = blk[have ? j : R4_PITCH - 1];
+                const float sign = (t & 1) ? 1.0f : -1.0f;
+                // linspace01(x, w) (usl_math.cuh), the division hoisted
+                const int x = k * R4_TILE + j;
+                const float xb = (x < w / 2) ? step * (float)x
+                                             : fmaf(-step, (float)(w - 1 - x), 1.0f);
+                unsigned cd, cu;
+                float4 c;
+                float cz, cw;
+                r4_decode(xb, sign * q.x, q.z, hwf, fw, cd, c.x, c.y);
+                r4_decode(xb, sign * q.y, q.w, hwf, fw, cu, cz, cw);
+                // Where a tap of term ud falls on a cell term dd updates in the
+                // same column, the later store must carry both parts: the loaded
+                // value of that cell is the same for both, so the walker
+                // subtracts (dd's part + ud's part) from it.
+                const float k0 = cu == cd ? c.x : (cu == cd + 1 ? c.y : 0.0f);
+                const float k1 = cu == cd ? c.y : (cu + 1 == cd ? c.x : 0.0f);
+                c.z = k0 + cz;
+                c.w = k1 + cw;
+                blk[have ? j : R4_PITCH - 1] = c;
+                reinterpret_cast<unsigned*>(blk + R4_TILE)[have ? j : 4 * (R4_PITCH - 1 - R4_TILE)] =
+                    cd | (cu << 16);
+            }
+            __syncwarp();
+            if (lane == 0) mb_arrive(full + st);
+            // refill the stage the walkers give back next
+            const int kn = k + R4_STAGES - 1;
+            if (kn < ntile) {
+                if (kn >= R4_STAGES) mb_wait(empty + kn % R4_STAGES, ((kn / R4_STAGES) - 1) & 1);
+                issue(kn);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
     } else if (warp < nwalk) {
         // ---- the walk ---------------------------------------------------------
         // Software pipeline over batches of 8 columns: the read-modify-writes
         // of batch i are interleaved with the staged loads of batch i + 1.
-        const uint32_t row_a = s_u32(H + (size_t)tid * HW);   // column -2 of the row
+        // the rows of a walking warp lie TRANSPOSED: cell (column x, lane t) at
+        // x * 32 + t, i.e. lane t only ever touches bank t -- conflict free
+        // wherever the 32 lanes' taps fall
+        const uint32_t row_a = s_u32(H + (size_t)warp * HW * 32 + lane);   // column -2 of the row
         constexpr int BPT = R4_TILE / R4_BATCH;               // batches per tile
         const int nbatch = (w + R4_BATCH - 1) / R4_BATCH;
 
@@ -240,8 +288,8 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
 #pragma unroll
             for (int u = 0; u < R4_BATCH; ++u) {
                 D.c[u] = a[u];
-                D.pd[u] = row_a + 4u * (ow[u] & 0xffffu);
-                D.pu[u] = row_a + 4u * (ow[u] >> 16);
+                D.pd[u] = row_a + 128u * (ow[u] & 0xffffu);
+                D.pu[u] = row_a + 128u * (ow[u] >> 16);
             }
         };
         auto acquire = [&](int bi) {
@@ -256,29 +304,26 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
                 if (lane == 0) mb_arrive(empty + (bi / BPT) % R4_STAGES);
             }
         };
-        // Both terms of a column as ONE chain: all loads, the sums of term dd
-        // forwarded where the taps of term ud coincide with them, stores in
-        // order.  (Explicit shared-memory instructions: the four loads must all
+        // Both terms of a column as ONE round trip: four loads, four adds, four
+        // stores, in that order (the preparing warps have folded term dd's part
+        // into term ud's where their taps coincide: the later store carries
+        // both).  Explicit shared-memory instructions: the four loads must all
         // be issued before the arithmetic -- left to itself the compiler sinks
-        // the second pair behind a branch, two round trips a column.)
+        // the second pair behind a branch, two round trips a column.
         auto rmw = [&](const R4Batch& D, int u) {
             const uint32_t pd = D.pd[u], pu = D.pu[u];
+            const float4 c = D.c[u];
             float d0, d1, u0, u1;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d0) : "r"(pd));
-            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(d1) : "r"(pd));
+            asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(d1) : "r"(pd));
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(u0) : "r"(pu));
-            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(u1) : "r"(pu));
-            const int diff = (int)(pu - pd);
-            d0 -= D.c[u].x; d1 -= D.c[u].y;
-            u0 = diff == 0 ? d0 : u0;
-            u0 = diff == 4 ? d1 : u0;
-            u1 = diff == 0 ? d1 : u1;
-            u1 = diff == -4 ? d0 : u1;
-            u0 -= D.c[u].z; u1 -= D.c[u].w;
+            asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(u1) : "r"(pu));
+            d0 -= c.x; d1 -= c.y;
+            u0 -= c.z; u1 -= c.w;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(pd), "f"(d0));
-            asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(pd), "f"(d1));
+            asm volatile("st.shared.f32 [%0+128], %1;" ::"r"(pd), "f"(d1));
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(pu), "f"(u0));
-            asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(pu), "f"(u1));
+            asm volatile("st.shared.f32 [%0+128], %1;" ::"r"(pu), "f"(u1));
         };
         // (columns past the end of a row were filled with zero contributions)
         R4Batch A, B;
@@ -313,43 +358,62 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
     __syncthreads();
 
     // ---- destination rows: H(y'-1), H(y'), H(y'+1) with the vertical weights ----
-    for (int yi = warp; yi < yb - ya; yi += R4_THREADS / 32) {
-        const int yd = ya + yi;
-        float wgt[3];
-        int row[3];
+    // A warp takes a block of 32 columns x 32 destination (row, view)s: lane =
+    // destination while it reads the transposed rows (three distinct banks per
+    // lane), lane = column while it writes to global memory; in between the
+    // block goes through a 32 x 33 tile of the ring's memory, which is free now.
+    {
+        float* tile = reinterpret_cast<float*>(stage) + (size_t)warp * (32 * 33);
+        const int ndest = (yb - ya) * 2;
+        const int nxb = (w + 31) / 32, nlb = (ndest + 31) / 32;
+        for (int blk = warp; blk < nxb * nlb; blk += R4_THREADS / 32) {
+            const int xb = (blk % nxb) * 32, lb = (blk / nxb) * 32;
+            const int L = lb + lane;
+            const int yd = ya + (L >> 1), o = L & 1;
+            float wgt[3];
+            const float* src[3];
 #pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-            const int rs = yd - 1 + kk;
-            wgt[kk] = 0.0f;
-            row[kk] = 0;
-            if (rs < 0 || rs >= h) continue;
-            row[kk] = rs - rs0;
-            const Tap2 ty = warp_row_taps(rs, h);
-            if (ty.i0 == yd) wgt[kk] = ty.w0;
-            else if (ty.i0 + 1 == yd) wgt[kk] = ty.w1;
-        }
-        for (int o = 0; o < 2; ++o) {
-            // (source view 1 - o scatters into destination view o)
-            const float* h0 = H + ((size_t)row[0] * 2 + (1 - o)) * HW + R4_PAD;
-            const float* h1 = H + ((size_t)row[1] * 2 + (1 - o)) * HW + R4_PAD;
-            const float* h2 = H + ((size_t)row[2] * 2 + (1 - o)) * HW + R4_PAD;
-            float* out = P.grad_disp + (long long)b * P.gd_bs + o * P.gd_cs + (long long)yd * w;
+            for (int kk = 0; kk < 3; ++kk) {
+                const int rs = yd - 1 + kk;
+                wgt[kk] = 0.0f;
+                int T = 0;
+                if (L < ndest && rs >= 0 && rs < h) {
+                    // (source view 1 - o scatters into destination view o)
+                    T = (rs - rs0) * 2 + (1 - o);
+                    const Tap2 ty = warp_row_taps(rs, h);
+                    if (ty.i0 == yd) wgt[kk] = ty.w0;
+                    else if (ty.i0 + 1 == yd) wgt[kk] = ty.w1;
+                }
+                src[kk] = H + (size_t)(T >> 5) * HW * 32 + (T & 31) + (size_t)(R4_PAD + xb) * 32;
+            }
+            const int nx = min(32, w - xb);
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                float v = 0.0f;
+                if (i < nx)
+                    v = wgt[0] * src[0][i * 32] + wgt[1] * src[1][i * 32] + wgt[2] * src[2][i * 32];
+                tile[lane * 33 + i] = v;
+            }
+            __syncwarp();
             // One add per destination element, by the only thread that owns it in
             // this launch, onto what an EARLIER launch stored: a reduction
             // instruction (no return value, the add happens in L2) gives the bits
             // of load-add-store without a round trip per element.
-            for (int x0 = lane; x0 < w; x0 += 256) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int x = x0 + 32 * u;
-                    if (x >= w) continue;
-                    const float v = wgt[0] * h0[x] + wgt[1] * h1[x] + wgt[2] * h2[x];
+            const int nd = min(32, ndest - lb);
+            if (lane < nx) {
+#pragma unroll 4
+                for (int j = 0; j < nd; ++j) {
+                    const int Lj = lb + j;
+                    float* out = P.grad_disp + (long long)b * P.gd_bs + (Lj & 1) * P.gd_cs +
+                                 (long long)(ya + (Lj >> 1)) * w + xb + lane;
+                    const float v = tile[j * 33 + lane];
                     if (P.accumulate)
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(out + x), "f"(v) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(out), "f"(v) : "memory");
                     else
-                        out[x] = v;
+                        *out = v;
                 }
             }
+            __syncwarp();
         }
     }
 }
@@ -362,7 +426,7 @@ int cons_rows_launch(MultiCons* C, cudaStream_t st) {
     for (int k = 0; k < C->n; ++k) {
         ConsParams& c = C->P[k];
         if (!c.scat || ((uintptr_t)c.scat & 15)) return USL_ERR_ARG;
-        const R4Geo g = r4_geometry(c.h, c.w, 210 * 1024);
+        const R4Geo g = r4_geometry(c.h, c.w, R4_SMEM_LIMIT);
         if (!g.nl) return USL_ERR_UNSUPPORTED;
         c.R = g.R;
         C->lanes[k] = g.nl;
@@ -374,7 +438,7 @@ int cons_rows_launch(MultiCons* C, cudaStream_t st) {
     //  flight on different streams)
     if (cudaFuncSetAttribute(cons_rows_kernel,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             210 * 1024) != cudaSuccess)
+                             R4_SMEM_LIMIT) != cudaSuccess)
         return USL_ERR_CUDA;
     cons_rows_kernel<<<C->cta_start[C->n], R4_THREADS, smem, st>>>(*C);
     return check_launch();

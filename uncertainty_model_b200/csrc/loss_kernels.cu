@@ -400,6 +400,7 @@ extern "C" int usl_loss_reduce(const float* partials, const int* cta_starts,
     for (int i = 0; i <= n_scales; ++i) st.v[i] = cta_starts[i];
     reduce_partials_kernel<<<n_scales * NUM_ACC, 256, 0, (cudaStream_t)stream>>>(
         partials, st, n_scales, sums);
+    mark(10, (cudaStream_t)stream);
     return check_launch();
 }
 
@@ -411,6 +412,7 @@ extern "C" int usl_loss_combine(const double* sums, const float* coef,
     DeviceGuard guard(sums);
     combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, coef, n_scales,
                                                        out_disp, out_err);
+    mark(11, (cudaStream_t)stream);
     return check_launch();
 }
 
@@ -584,6 +586,7 @@ extern "C" int usl_loss_grad_sharded(const UslLossConfig* cfgs,
     for (int i = 0; i <= n_scales; ++i) st.v[i] = cta_starts[i];
     reduce_partials_kernel<<<n_scales * NUM_ACC, 256, 0, (cudaStream_t)reduce_stream>>>(
         partials, st, n_scales, sums);
+    mark(10, (cudaStream_t)reduce_stream);
     return check_launch();
 }
 

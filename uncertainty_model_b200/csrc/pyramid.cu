@@ -106,7 +106,9 @@ extern "C" int usl_pyramid(const float* src, int B, int C, int H, int W,
         if (p.cta_start[l] + ctas > 0x7fffffffLL) return USL_ERR_UNSUPPORTED;
         p.cta_start[l + 1] = p.cta_start[l] + (int)ctas;
     }
+    mark(0, (cudaStream_t)stream);
     pyramid_kernel<<<(unsigned)p.cta_start[p.levels], PYR_THREADS, 0,
                      (cudaStream_t)stream>>>(p);
+    mark(1, (cudaStream_t)stream);
     return check_launch();
 }

@@ -94,6 +94,13 @@ inline const Knobs& knobs() {
     return k;
 }
 
+// Profiling aid (usl_debug_timeline): when a buffer is registered, `mark`
+// enqueues a one-thread kernel that writes %globaltimer into slot `idx` -- a
+// time line of the concurrent per-scale launches that also works inside a CUDA
+// graph replay (ncu serialises the launches, events do not exist in a graph).
+std::atomic<unsigned long long*>& timeline_buffer();
+void mark(int idx, cudaStream_t st);
+
 // Every entry point launches on the device that owns its tensors: the guard
 // makes that device current for the call and restores the caller's afterwards
 // (the reference's DDP launcher moves everything `.to(cuda:i)` without ever
