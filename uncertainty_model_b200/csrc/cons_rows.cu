@@ -109,6 +109,16 @@ __device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
         "R4_DONE:\n"
         "}" ::"r"(s_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ int mb_test(uint64_t* bar, uint32_t parity) {
+    int ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}" : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    return ok;
+}
 // c_warp_coord of col_core.cuh (same operations in the same order: the sampling
 // column comes out bit-identical to the one the column kernels used)
 __device__ __forceinline__ float r4_coord(float xbase, float shift, float half_n) {
@@ -217,15 +227,42 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
                              "l"(src), "r"(in ? 16 : 0) : "memory");
             }
         };
-        // (a group is committed per tile slot whether or not it holds copies, so
-        //  that "all but the newest R4_STAGES - 2 groups" always means tile k)
-        for (int k = 0; k < R4_STAGES - 1; ++k) {
-            if (k < ntile) issue(k);
+        // One copy group per tile, in tile order.  A stage is refilled as soon as
+        // the walkers have given it back -- tested without blocking before every
+        // tile, so that decoding runs up to R4_STAGES - 1 tiles ahead of the walk
+        // instead of waiting for the walkers after each tile; the only blocking
+        // wait is for the stage of the tile that is to be decoded next.
+        int issued = 0;
+        auto refill = [&](bool must) -> bool {
+            // tile `issued` goes into the stage tile `issued - R4_STAGES` had
+            if (issued >= R4_STAGES) {
+                uint64_t* bar = empty + issued % R4_STAGES;
+                const uint32_t parity = ((issued / R4_STAGES) - 1) & 1;
+                if (must) {
+                    mb_wait(bar, parity);
+                } else {
+                    int ok = 0;
+                    if (lane == 0) ok = mb_test(bar, parity);
+                    if (!__shfl_sync(0xffffffffu, ok, 0)) return false;
+                }
+            }
+            issue(issued);
             asm volatile("cp.async.commit_group;" ::: "memory");
-        }
+            ++issued;
+            return true;
+        };
         for (int k = 0; k < ntile; ++k) {
             const int st = k % R4_STAGES;
-            asm volatile("cp.async.wait_group %0;" ::"n"(R4_STAGES - 2) : "memory");
+            if (issued <= k) refill(true);
+            while (issued < ntile && issued < k + R4_STAGES && refill(false)) {}
+            // tile k's copies (this thread's) have landed when only the groups
+            // committed after it are still pending
+            switch (issued - 1 - k) {
+                case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+                case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+                case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+                default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+            }
 #pragma unroll
             for (int i = 0; i < R4_MAXE; ++i) {
                 const int e = gt + i * gn;
@@ -257,13 +294,6 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
             }
             __syncwarp();
             if (lane == 0) mb_arrive(full + st);
-            // refill the stage the walkers give back next
-            const int kn = k + R4_STAGES - 1;
-            if (kn < ntile) {
-                if (kn >= R4_STAGES) mb_wait(empty + kn % R4_STAGES, ((kn / R4_STAGES) - 1) & 1);
-                issue(kn);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         }
     } else if (warp < nwalk) {
         // ---- the walk ---------------------------------------------------------
