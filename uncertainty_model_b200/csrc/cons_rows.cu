@@ -396,6 +396,9 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
         float* tile = reinterpret_cast<float*>(stage) + (size_t)warp * (32 * 33);
         const int ndest = (yb - ya) * 2;
         const int nxb = (w + 31) / 32, nlb = (ndest + 31) / 32;
+        // rows of the gradient 16-byte aligned: whole quads of columns
+        const bool vec_ok = (w % 4 == 0) && (((uintptr_t)P.grad_disp & 15) == 0) &&
+                            (((P.gd_bs | P.gd_cs) & 3) == 0);
         for (int blk = warp; blk < nxb * nlb; blk += R4_THREADS / 32) {
             const int xb = (blk % nxb) * 32, lb = (blk / nxb) * 32;
             const int L = lb + lane;
@@ -430,7 +433,29 @@ cons_rows_kernel(const __grid_constant__ MultiCons M) {
             // instruction (no return value, the add happens in L2) gives the bits
             // of load-add-store without a round trip per element.
             const int nd = min(32, ndest - lb);
-            if (lane < nx) {
+            if (vec_ok) {
+                // four columns a lane, four destinations a warp instruction:
+                // 128-bit reductions (REDG.ADD.F32x4), a quarter of the lane
+                // operations the L2 reduction path is limited by
+                const int jj = lane >> 3, x4 = 4 * (lane & 7);
+                if (x4 < nx) {
+#pragma unroll 2
+                    for (int j0 = 0; j0 < nd; j0 += 4) {
+                        const int j = j0 + jj;
+                        if (j >= nd) break;
+                        const int Lj = lb + j;
+                        float* out = P.grad_disp + (long long)b * P.gd_bs + (Lj & 1) * P.gd_cs +
+                                     (long long)(ya + (Lj >> 1)) * w + xb + x4;
+                        const float* tp = tile + j * 33 + x4;
+                        const float v0 = tp[0], v1 = tp[1], v2 = tp[2], v3 = tp[3];
+                        if (P.accumulate)
+                            asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(out),
+                                         "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+                        else
+                            *reinterpret_cast<float4*>(out) = make_float4(v0, v1, v2, v3);
+                    }
+                }
+            } else if (lane < nx) {
 #pragma unroll 4
                 for (int j = 0; j < nd; ++j) {
                     const int Lj = lb + j;
