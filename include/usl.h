@@ -211,9 +211,10 @@ int usl_loss_grad(const UslLossConfig* cfgs, const UslLossScale* scales,
  * gradients, AND usl_loss_reduce(partials, cta_starts, n_scales, sums)
  * enqueued on `reduce_stream` behind the column kernels only -- not behind the
  * transposed warps, which need another ~25 % of the step.  The caller enqueues
- * its exchange of `sums` between ranks behind `reduce_stream` and joins it to
- * `stream` before usl_loss_combine; the exchange then runs beside the
- * transposed warp.  reduce_stream: a cudaStream_t of the same device, different
+ * its exchange of `sums` between ranks and usl_loss_combine behind
+ * `reduce_stream` and joins it to `stream`; both then run beside the
+ * transposed warp (worth it on one GPU too: the reduction and the combination
+ * leave the critical path).  reduce_stream: a cudaStream_t of the same device, different
  * from `stream` (it is made to wait for work forked from `stream`, so it takes
  * part in a stream capture of `stream`).  USL_ERR_UNSUPPORTED where
  * usl_loss_grad would not run its per-scale transposed warps (the caller then

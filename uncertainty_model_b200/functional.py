@@ -226,13 +226,13 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
     coef = coef_tensor(tuple(tuple(k * cscale for k in c.coef) for c in cfgs),
                        device)
     stream = _stream(partials)
-    # sharded batch + gradients: the all-reduce of the sums only needs the
-    # column kernels, so it runs (side stream -> NCCL stream) beside the
-    # transposed warps
+    # With gradients: the reduction of the term sums, their exchange between
+    # ranks (sharded batch) and the combination only need the column kernels, so
+    # they run on a side stream (-> NCCL stream -> side stream) beside the
+    # transposed warps and are joined at the end.
     split = with_grad and reduce_group is not None
     starts_arr = (C.c_int * (n + 1))(*starts)
-    done = False
-    if split:
+    if with_grad:
         side = _reduce_stream(partials.device)
         rc = L.usl_loss_grad_sharded(cfg_arr, sc_arr, n, partials.data_ptr(),
                                      starts_arr, sums.data_ptr(),
@@ -240,13 +240,14 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
         if rc != _lib.USL_ERR_UNSUPPORTED:
             check(rc, 'usl_loss_grad_sharded')
             with torch.cuda.stream(side):
-                work = torch.distributed.all_reduce(sums, group=reduce_group,
-                                                    async_op=True)
-            work.wait()     # the caller's stream waits for the collective
-            done = True
-    if done:
-        pass
-    elif with_grad:
+                if reduce_group is not None:
+                    torch.distributed.all_reduce(sums, group=reduce_group)
+                check(L.usl_loss_combine(sums.data_ptr(), coef.data_ptr(), n,
+                                         out_disp.data_ptr(),
+                                         out_err.data_ptr(), side.cuda_stream),
+                      'usl_loss_combine')
+            torch.cuda.current_stream(partials.device).wait_stream(side)
+            return out_disp, out_err, sums
         check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None,
                               partials.data_ptr(),
                               GRAD_DEFER_SCATTER0 if split else 0, stream),
@@ -254,17 +255,16 @@ def loss_forward(cfgs: Sequence[UslLossConfig],
     else:
         check(L.usl_loss_fwd(cfg_arr, sc_arr, n, partials.data_ptr(), stream),
               'usl_loss_fwd')
-    if not done:
-        check(L.usl_loss_reduce(partials.data_ptr(), starts_arr, n,
-                                sums.data_ptr(), stream), 'usl_loss_reduce')
-        if split:
-            work = torch.distributed.all_reduce(sums, group=reduce_group,
-                                                async_op=True)
-            check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None, None,
-                                  GRAD_ONLY_SCATTER0, stream), 'usl_loss_grad')
-            work.wait()
-        elif reduce_group is not None:
-            torch.distributed.all_reduce(sums, group=reduce_group)
+    check(L.usl_loss_reduce(partials.data_ptr(), starts_arr, n,
+                            sums.data_ptr(), stream), 'usl_loss_reduce')
+    if split:
+        work = torch.distributed.all_reduce(sums, group=reduce_group,
+                                            async_op=True)
+        check(L.usl_loss_grad(cfg_arr, sc_arr, n, None, None, None,
+                              GRAD_ONLY_SCATTER0, stream), 'usl_loss_grad')
+        work.wait()
+    elif reduce_group is not None:
+        torch.distributed.all_reduce(sums, group=reduce_group)
     check(L.usl_loss_combine(sums.data_ptr(), coef.data_ptr(), n,
                              out_disp.data_ptr(), out_err.data_ptr(), stream),
           'usl_loss_combine')
@@ -276,8 +276,9 @@ _REDUCE_STREAMS = {}
 
 
 def _reduce_stream(device) -> 'torch.cuda.Stream':
-    """Per-device side stream on which the term sums of a sharded batch are
-    reduced and handed to the collective (usl_loss_grad_sharded)."""
+    """Per-device side stream on which the term sums are reduced, exchanged
+    between ranks (sharded batch) and combined beside the transposed warps
+    (usl_loss_grad_sharded)."""
     key = (device.type, device.index)
     st = _REDUCE_STREAMS.get(key)
     if st is None:
