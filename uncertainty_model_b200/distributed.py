@@ -2,9 +2,9 @@
 
 The path shards over samples with no data exchange: every rank runs the fused
 kernels on its own shard.  The only collective is one NCCL all-reduce of the
-raw per-term sums (fp64, scales x 6 values) per step -- issued between the
-fused forward launch and the 2-float combine kernel, on the same stream, with
-no host synchronisation -- so that every rank reports the loss of the GLOBAL
+raw per-term sums (fp64, scales x 6 values) per step -- issued behind the
+column kernels on a high-priority side stream, beside the transposed warps,
+with no host synchronisation -- so that every rank reports the loss of the GLOBAL
 batch (the reference leaves the loss un-reduced, parallel_main.py:156-160:
 rank 0 logs its own shard's).
 

@@ -282,7 +282,9 @@ def _reduce_stream(device) -> 'torch.cuda.Stream':
     key = (device.type, device.index)
     st = _REDUCE_STREAMS.get(key)
     if st is None:
-        st = _REDUCE_STREAMS[key] = torch.cuda.Stream(device)
+        # (high priority: its few CTAs go ahead of the pending CTAs of the
+        #  transposed-warp kernels)
+        st = _REDUCE_STREAMS[key] = torch.cuda.Stream(device, priority=-1)
     return st
 
 
