@@ -73,11 +73,13 @@ def main():
          'col_kernel<528,GRAD,PLAIN,hot terms>: steady-state loop (two rows per trip)')
     ins_r, _ = loops('cons_rows.o', 'cons_rows_kernel')
 
-    def walk(found):        # the loop with the chain's selects and no global loads
-        best = None
+    def walk(found):        # the loop of scalar read-modify-writes: no global
+        best = None         # loads, no reductions, >= 32 shared stores
         for lo, hi, n in found:
             _, _, count, _, _ = sm.model(ins_r, lo, hi)
-            if count['LDG'] == 0 and count['FSEL'] >= 32 and (best is None or n < best[2]):
+            if count['LDG'] == 0 and count['REDG'] == 0 and count['LDGSTS'] == 0 \
+                    and count['STS'] >= 32 and count['FADD'] >= 32 \
+                    and (best is None or n < best[2]):
                 best = (lo, hi, n)
         return best
     dump('r02_sass_cons_rows_walk_loop.txt', 'cons_rows.o', 'cons_rows_kernel', walk,
