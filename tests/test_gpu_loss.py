@@ -378,6 +378,39 @@ def test_benchmark_shapes_elementwise(dev, name):
     parity.record(name, stats)
 
 
+@pytest.mark.parametrize('shape', [(3, 40, 72, 'l1'), (16, 256, 512, 'bayesian')])
+def test_mirror_and_view_swap_symmetry(dev, shape):
+    """Size-independent property (holds for the reference's formulas; checked
+    on the fp64 oracle in tests/test_oracle.py): mirror every image left-right
+    and swap the two views -- the stereo geometry is the same scene seen in a
+    mirror, so both losses are unchanged and the gradients are the mirrored,
+    swapped ones.  Run at the benchmark shape too.  fp32 rounds the mirrored
+    coordinates differently, so a few taps flip: losses to 1e-5, gradients
+    element-wise on all but 1 % of the elements."""
+    from oracle.make_golden import loss_config, make_inputs
+    b, h, w, lt = shape
+    cfg = loss_config(lt, smoothness_weight=0.25)
+    left, right, preds = make_inputs(b, h, w, 0.3, 23)
+
+    def mirrored(p):
+        return torch.stack([p[:, 1].flip(2), p[:, 0].flip(2),
+                            p[:, 3].flip(2), p[:, 2].flip(2)], 1).contiguous()
+
+    dl, el, gp, *_ = run_ours(dev, torch.cat([left, right], 1), preds, cfg)
+    dl2, el2, gp2, *_ = run_ours(
+        dev, torch.cat([right.flip(3), left.flip(3)], 1).contiguous(),
+        [mirrored(p) for p in preds], cfg)
+    assert abs(dl.item() - dl2.item()) <= LOSS_REL * abs(dl.item())
+    assert abs(el.item() - el2.item()) <= LOSS_REL * abs(el.item())
+    for a, b2 in zip(gp, gp2):
+        ga = a.grad
+        gb = mirrored(b2.grad)
+        for c in range(4):
+            scale = ga[:, c].abs().max().item()
+            off = ((ga[:, c] - gb[:, c]).abs() > parity.ELEM_REL * scale)
+            assert off.float().mean().item() < 0.01
+
+
 def test_batch_shard_additivity(dev):
     """loss(B) equals the mean of the shard losses and the
     raw term sums add up -- the property the multi-GPU path relies on."""

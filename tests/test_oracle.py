@@ -256,3 +256,29 @@ def test_heatmap_port_indexing_rule():
     x = torch.tensor([[[0.0, 1.0, -0.1, 2.0, float('nan'), 0.5, 255.0 / 256]]])
     out = PP.to_heatmap(x, table)[0].numpy().ravel()      # R channel = 3 * index
     assert list(out) == [0.0, 765.0, 0.0, 765.0, 0.0, 384.0, 765.0]
+
+
+@pytest.mark.parametrize('loss_type', ['l1', 'bayesian', 'log_bayesian'])
+def test_mirror_and_view_swap_symmetry_of_the_port(loss_type):
+    """The property tests/test_gpu_loss.py::test_mirror_and_view_swap_symmetry
+    checks on the GPU at the benchmark shape, established here on the fp64
+    port: mirroring the images left-right and swapping the views leaves both
+    losses unchanged and mirrors + swaps the gradients."""
+    import torch
+    from oracle import loss_port as P
+    from oracle.make_golden import loss_config, make_inputs
+    cfg = loss_config(loss_type, smoothness_weight=0.25)
+    left, right, preds = make_inputs(2, 32, 64, 0.3, 7)
+
+    def mirrored(p):
+        return torch.stack([p[:, 1].flip(2), p[:, 0].flip(2),
+                            p[:, 3].flip(2), p[:, 2].flip(2)], 1)
+
+    preds = [p.double() for p in preds]
+    dl, el, g = P.step(torch.cat([left, right], 1).double(), preds, cfg)
+    dl2, el2, g2 = P.step(torch.cat([right.flip(3), left.flip(3)], 1).double(),
+                          [mirrored(p) for p in preds], cfg)
+    assert abs(float(dl) - float(dl2)) <= 1e-7 * abs(float(dl))
+    assert abs(float(el) - float(el2)) <= 1e-7 * abs(float(el))
+    for a, b in zip(g, g2):
+        assert float((a - mirrored(b)).norm() / a.norm()) <= 1e-5

@@ -57,7 +57,6 @@ struct Knobs {
     int col_only;        // USL_COL_ONLY: bit mask of the scales to launch
     int col_serial;      // USL_COL_SERIAL: all scales on the caller's stream
     int col_no_priority; // USL_COL_NO_PRIORITY
-    int col_queue;       // USL_COL_QUEUE: persistent work-queue launch (0/1, -1 auto)
     int fwd_tw, fwd_r, bwd_tw, bwd_r;   // USL_{FWD,BWD}_{TW,R}: general kernels
     int cons_r;          // USL_CONS_R
     int scatter_v1;      // USL_SCATTER_V1
@@ -79,7 +78,6 @@ inline const Knobs& knobs() {
         x.col_only = knob_int("USL_COL_ONLY", 0xff);
         x.col_serial = knob_int("USL_COL_SERIAL", 0);
         x.col_no_priority = knob_int("USL_COL_NO_PRIORITY", 0);
-        x.col_queue = knob_int("USL_COL_QUEUE", -1);
         x.fwd_tw = knob_int("USL_FWD_TW", 0);
         x.fwd_r = knob_int("USL_FWD_R", 0);
         x.bwd_tw = knob_int("USL_BWD_TW", 0);
