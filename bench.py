@@ -5,7 +5,14 @@
 A "step" is one pass of the hot path over one synthetic batch, exactly as the
 training loop runs it (reference train.py:117-128): scale_pyramid ->
 reconstruct_pyramid -> TukraUncertaintyLoss forward -> backward, through the
-drop-in classes (i.e. through the C ABI of libusl.so).
+drop-in classes (i.e. through the C ABI of libusl.so).  The backward hands the
+gradients w.r.t. the predictions on, as it does in the training loop where the
+predictions are the decoder's outputs: `torch.autograd.grad(disp_loss +
+error_loss, predictions)`.  (`(disp_loss + error_loss).backward()` with the
+predictions as LEAF tensors makes autograd clone every gradient into `.grad`
+inside a captured graph -- 89 MB of copies, ~19 us a step, that belong to the
+benchmark's leaves and not to the path; that variant is measured too and
+reported as `leaf_backward_value`.)
 
 Main line: BASELINE.json configs[1] -- bayesian uncertainty loss, batch 16
 synthetic 256x512 stereo pairs per GPU, 4 scales (the configuration the metric
@@ -241,6 +248,7 @@ class Harness:
             self.disc = FixedGradientDiscriminator(b, h, w).to(dev)
         self.graphs = None
         self.graph_outs = None
+        self.grads = [None] * nsets
 
     def _views(self, flat):
         b, h, w = self.shape
@@ -258,17 +266,21 @@ class Harness:
     def h2d_bytes(self):
         return self.host[0].numel() * 4
 
-    def step(self, k):
+    def step(self, k, leaf_backward=False):
         _, stereo, preds = self.sets[k % self.nsets]
         U = self.U
-        for p in preds:
-            p.grad = None
         pyr = U.scale_pyramid(stereo, 4)
         rec = U.reconstruct_pyramid(preds, pyr)
         # (adversarial = BASELINE config 4: the loss hands the reconstructions
         #  to the discriminator and a gradient arrives at them from it)
         dl, el = self.fn(pyr, preds, rec, 0, self.disc)
-        (dl + el).backward()
+        if leaf_backward:
+            for p in preds:
+                p.grad = None
+            (dl + el).backward()
+        else:
+            # the gradients w.r.t. the predictions, handed on (module docstring)
+            self.grads[k % self.nsets] = torch.autograd.grad(dl + el, preds)
         return dl, el
 
     def capture(self):
@@ -277,11 +289,28 @@ class Harness:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
+                # Fresh leaves for the predictions, made on the capture stream:
+                # autograd binds a leaf's gradient accumulation to the stream
+                # that was current when the leaf was first used, and the eager
+                # warm-up steps ran on the default stream -- the graph would
+                # carry a cross-stream synchronisation after every backward that
+                # a training loop (where the predictions are not leaves) does
+                # not have.
+                self.sets = [(flat, stereo,
+                              [p.detach().requires_grad_(True) for p in preds])
+                             for flat, stereo, preds in self.sets]
                 for s in range(self.nsets):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=side):
                         outs.append(self.step(s))
                     graphs.append(g)
+                self.leaf_graphs = []
+                for s in range(self.nsets):
+                    self.step(s, leaf_backward=True)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        self.step(s, leaf_backward=True)
+                    self.leaf_graphs.append(g)
             torch.cuda.current_stream().wait_stream(side)
             for g in graphs:
                 g.replay()
@@ -377,6 +406,10 @@ def measure(hz, steps, warmup, world, dev, e2e=True):
            'library_launches_per_step': ours,
            'launch': 'cuda-graph replay' if hz.graphs is not None else 'eager'}
     out['ms_eager'] = timed(hz.step, steps, world, dev) / steps
+    if hz.graphs is not None and getattr(hz, 'leaf_graphs', None):
+        out['ms_leaf_backward'] = timed(
+            lambda i: hz.leaf_graphs[i % hz.nsets].replay(), steps, world,
+            dev) / steps
     if not e2e:
         return out
     # ---- e2e: host inputs, H2D + step + D2H of the losses every step ------
@@ -474,6 +507,8 @@ def run_ours(args, rank, world, local_rank):
                    'l2': f'inputs rotate over {args.sets} sets '
                          f'({args.sets * hz.h2d_bytes / 1e6:.0f} MB) > 126 MB L2'},
         'eager_value': world * pixels / (m['ms_eager'] * 1e-3) / 1e6,
+        'leaf_backward_value': (world * pixels / (m['ms_leaf_backward'] * 1e-3) / 1e6
+                                if 'ms_leaf_backward' in m else None),
         'e2e': {'value': world * pixels / (m['ms_e2e'] * 1e-3) / 1e6,
                 'unit': UNIT, 'h2d_bytes_per_step': hz.h2d_bytes,
                 'd2h_bytes_per_step': 8, 'ms_per_step': m['ms_e2e'],

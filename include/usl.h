@@ -57,7 +57,7 @@ long long usl_launch_count(void);
  * (ns) into it around the launches of a training step: 0/1 before/after the
  * pyramid kernel, 2+i after scale i's fused kernel, 6+i after its transposed
  * warp, 10 after the reduction, 11 after the combination, 12 after the
- * rescale.  Works inside a CUDA-graph replay (tools/step_timeline.py). */
+ * rescale; 13 / 14 = the start and the last stamp of the step before.  Works inside a CUDA-graph replay (tools/step_timeline.py). */
 #define USL_TIMELINE_SLOTS 16
 int usl_debug_timeline(void* slots);
 

@@ -35,6 +35,8 @@ def main():
     ap.add_argument('--width', type=int, default=512)
     ap.add_argument('--loss', default='bayesian')
     ap.add_argument('--reps', type=int, default=40)
+    ap.add_argument('--steps-per-graph', type=int, default=1)
+    ap.add_argument('--mode', default='backward', choices=['backward', 'grad', 'forward'])
     a = ap.parse_args()
     dev = torch.device('cuda:0')
     torch.manual_seed(0)
@@ -47,13 +49,19 @@ def main():
                  .requires_grad_() for i in range(4)]
         sets.append((st, preds))
     slots = torch.zeros(16, dtype=torch.int64, device=dev)
+    keep = []
 
     def step(k):
         st, preds = sets[k]
+        for p in preds:
+            p.grad = None
         pyr = U.scale_pyramid(st, 4)
         rec = U.reconstruct_pyramid(preds, pyr)
         dl, el = fn(pyr, preds, rec, 1, None)
-        (dl + el).backward()
+        if a.mode == 'backward':
+            (dl + el).backward()
+        elif a.mode == 'grad':
+            keep[:] = torch.autograd.grad(dl + el, preds)
 
     for k in range(4):
         step(k)
@@ -63,12 +71,16 @@ def main():
     if not a.eager:
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
+            # (fresh leaves on the capture stream: see bench.py, Harness.capture)
+            sets[:] = [(st, [p.detach().requires_grad_(True) for p in preds])
+                       for st, preds in sets]
             for k in range(4):
                 step(k)
             for k in range(4):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    step(k)
+                    for j in range(a.steps_per_graph):
+                        step((k + j) % 4)
                 graphs.append(g)
         torch.cuda.synchronize()
     rows = []
@@ -81,6 +93,15 @@ def main():
             step(r % 4)
         torch.cuda.synchronize()
         rows.append(slots.cpu().tolist())
+    # back-to-back replays: the period of a step and the gap between the end
+    # of one step and the start of the next (slots 13 / 14)
+    if graphs:
+        for r in range(8):
+            graphs[r % 4].replay()
+        torch.cuda.synchronize()
+        v = slots.cpu().tolist()
+        print(f'back to back: period {(v[0] - v[13]) * 1e-3:.1f} us, '
+              f'last stamp of the previous step -> this start {(v[0] - v[14]) * 1e-3:.1f} us')
     _lib.check(_lib.lib().usl_debug_timeline(None))
     t = torch.tensor(rows[4:], dtype=torch.float64)
     t0 = t[:, 0:1]

@@ -84,6 +84,11 @@ std::atomic<unsigned long long*>& timeline_buffer() {
 __global__ void stamp_kernel(unsigned long long* buf, int idx) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (idx == 0) {     // the previous step's start and its last stamp
+        unsigned long long last = 0;
+        for (int i = 1; i <= 12; ++i) last = buf[i] > last ? buf[i] : last;
+        buf[13] = buf[0]; buf[14] = last;
+    }
     buf[idx] = t;
 }
 void mark(int idx, cudaStream_t st) {
