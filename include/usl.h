@@ -81,6 +81,17 @@ int usl_warp_bwd_disp(const float* disp, long long disp_bs, float sign,
                       int B, int C, int h, int w, float* grad_disp,
                       long long gd_bs, void* stream);
 
+/* gradient of the above w.r.t. the SAMPLED image (the reference's op is
+ * differentiable there too, utils.py:96-97: ATen's grid_sampler_2d_backward with
+ * float atomics; here deterministic, in two launches).  workspace:
+ * usl_warp_bwd_image_workspace_bytes(B, C, h, w) bytes, contents irrelevant. */
+long long usl_warp_bwd_image_workspace_bytes(int B, int C, int h, int w);
+int usl_warp_bwd_image(const float* disp, long long disp_bs, float sign,
+                       const float* grad_out, long long go_bs, long long go_cs,
+                       int B, int C, int h, int w, void* workspace,
+                       float* grad_image, long long gi_bs, long long gi_cs,
+                       void* stream);
+
 /* ---- train/loss.py  fused per-scale loss ----------------------------------
  * Term bits (UslLossConfig.terms) and the index of their raw sum in `sums`: */
 #define USL_TERM_REPROJ 1u   /* [0] WeightedSSIMLoss            loss.py:133-151 */

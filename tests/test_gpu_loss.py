@@ -123,6 +123,42 @@ def test_reconstruct_matches_reference(dev):
     assert torch.equal(gen, left)
 
 
+@pytest.mark.parametrize('shape', [(2, 3, 32, 48, 0.5), (1, 1, 17, 37, 1.0),
+                                   (2, 3, 64, 512, 0.3)])
+def test_reconstruct_is_differentiable_in_the_sampled_image(dev, shape):
+    """utils.py:96-97: the reference's grid_sample is differentiable w.r.t. the
+    image it samples as well.  Against torch autograd on the fp64 port; and
+    the transposed warp is deterministic (ATen's uses float atomics)."""
+    from oracle import loss_port as P
+    from uncertainty_model_b200.train import utils as U
+    b, c, h, w, scale = shape
+    g = torch.Generator().manual_seed(11)
+    disp = scale * torch.rand(b, 1, h, w, generator=g) - 0.25 * scale
+    image = torch.rand(b, c, h, w, generator=g)
+    upstream = torch.randn(b, c, h, w, generator=g)
+    d64 = disp.double().requires_grad_(True)
+    i64 = image.double().requires_grad_(True)
+    (P.warp(d64, i64) * upstream.double()).sum().backward()
+    outs = []
+    for _ in range(2):
+        dd = disp.to(dev).requires_grad_(True)
+        ii = image.to(dev).requires_grad_(True)
+        out = U.reconstruct(dd, ii)
+        (out * upstream.to(dev)).sum().backward()
+        outs.append((dd.grad.clone(), ii.grad.clone()))
+    gd, gi = outs[0]
+    # (the tap weights come from an fp32 sampling coordinate of magnitude w:
+    #  their absolute error grows with the width, 512 * 2^-24 = 3e-5)
+    err = rel_l2(gi.cpu().numpy(), i64.grad.numpy())
+    worst = np.abs(gi.cpu().numpy() - i64.grad.numpy()).max() / \
+        float(i64.grad.abs().max())
+    print('image gradient: rel-L2', err, 'worst element', worst)
+    assert err <= 1e-5 * max(1.0, w / 48)
+    assert worst <= 2e-5 * max(1.0, w / 48)
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[1][0])
+
+
 def test_reconstruct_pyramid_is_lazy_and_differentiable(dev):
     from oracle import loss_port as P
     from oracle.make_golden import make_inputs

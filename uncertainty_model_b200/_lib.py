@@ -74,6 +74,13 @@ SIGNATURES = {
                                     C.c_longlong, C.c_longlong, C.c_int,
                                     C.c_int, C.c_int, C.c_int, _f32p,
                                     C.c_longlong, C.c_void_p]),
+    'usl_warp_bwd_image_workspace_bytes': (C.c_longlong, [C.c_int, C.c_int,
+                                                          C.c_int, C.c_int]),
+    'usl_warp_bwd_image': (C.c_int, [_f32p, C.c_longlong, C.c_float, _f32p,
+                                     C.c_longlong, C.c_longlong, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     _f32p, C.c_longlong, C.c_longlong,
+                                     C.c_void_p]),
     'usl_loss_plan': (C.c_int, [C.POINTER(UslLossConfig),
                                 C.POINTER(UslLossScale), C.c_int, C.c_int,
                                 C.POINTER(C.c_int)]),

@@ -75,7 +75,98 @@ static int launch_warp(const WarpParams& p, bool backward, void* stream) {
     return check_launch();
 }
 
+// ---- gradient w.r.t. the SAMPLED image (the transpose of the gather) --------
+// ATen does it with float atomics.  Here, deterministic: one thread per (b, c,
+// output row y) adds the horizontal taps of its row, in column order, into a
+// private row of the workspace (columns -2 .. w+1: taps outside the image land
+// in pads); a second launch blends the three rows around each image row with
+// the vertical tap weights, in row order.  Not a hot path (the training step
+// differentiates through a sampled map only inside ConsistencyLoss, which the
+// fused kernels handle): plain global-memory read-modify-writes.
+constexpr int WBI_PAD = 2;
+
+__global__ void __launch_bounds__(128)
+warp_bwd_image_rows_kernel(const WarpParams p, float* __restrict__ ws) {
+    const long long rows = (long long)p.B * p.C * p.h;
+    const int pitch = p.w + 2 * WBI_PAD;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(r % p.h);
+        const int c = (int)((r / p.h) % p.C);
+        const int b = (int)(r / ((long long)p.h * p.C));
+        float* T = ws + r * pitch;
+        for (int i = 0; i < pitch; ++i) T[i] = 0.0f;
+        const float* d = p.disp + b * p.disp_bs + (long long)y * p.w;
+        const float* go = p.grad_out + b * p.go_bs + c * p.go_cs + (long long)y * p.w;
+        for (int x = 0; x < p.w; ++x) {
+            const Tap2 tx = split_coord(warp_coord(x, p.w, p.sign * __ldg(d + x)));
+            const float f = fminf(fmaxf((float)tx.i0, (float)-WBI_PAD), (float)p.w);
+            const int col = (int)f + WBI_PAD;
+            const float g = __ldg(go + x);
+            T[col] += g * tx.w0;
+            T[col + 1] += g * tx.w1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+warp_bwd_image_blend_kernel(const WarpParams p, const float* __restrict__ ws,
+                            float* __restrict__ gi, long long gi_bs, long long gi_cs) {
+    const long long total = (long long)p.B * p.C * p.h * p.w;
+    const int pitch = p.w + 2 * WBI_PAD;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % p.w);
+        const int yy = (int)((i / p.w) % p.h);
+        const long long plane = i / ((long long)p.w * p.h);     // b * C + c
+        const int c = (int)(plane % p.C), b = (int)(plane / p.C);
+        float acc = 0.0f;
+        for (int y = yy - 1; y <= yy + 1; ++y) {
+            if (y < 0 || y >= p.h) continue;
+            const Tap2 ty = warp_row_taps(y, p.h);
+            float wgt = 0.0f;
+            if (ty.i0 == yy) wgt = ty.w0;
+            else if (ty.i0 + 1 == yy) wgt = ty.w1;
+            acc += wgt * ws[(plane * p.h + y) * pitch + x + WBI_PAD];
+        }
+        gi[b * gi_bs + c * gi_cs + (long long)yy * p.w + x] = acc;
+    }
+}
+
 }  // namespace usl
+
+extern "C" long long usl_warp_bwd_image_workspace_bytes(int B, int C, int h, int w) {
+    if (B <= 0 || C <= 0 || h <= 0 || w <= 0) return 0;
+    return (long long)B * C * h * (w + 2 * usl::WBI_PAD) * (long long)sizeof(float);
+}
+
+extern "C" int usl_warp_bwd_image(const float* disp, long long disp_bs, float sign,
+                                  const float* grad_out, long long go_bs,
+                                  long long go_cs, int B, int C, int h, int w,
+                                  void* workspace, float* grad_image,
+                                  long long gi_bs, long long gi_cs, void* stream) {
+    if (!disp || !grad_out || !workspace || !grad_image || B <= 0 || C <= 0 ||
+        h < 1 || w < 1)
+        return USL_ERR_ARG;
+    usl::DeviceGuard guard(grad_out);
+    usl::WarpParams p = {};
+    p.disp = disp; p.disp_bs = disp_bs; p.sign = sign;
+    p.grad_out = grad_out; p.go_bs = go_bs; p.go_cs = go_cs;
+    p.B = B; p.C = C; p.h = h; p.w = w;
+    const long long rows = (long long)B * C * h;
+    long long blocks = (rows + 127) / 128;
+    const long long cap = (long long)usl::num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    usl::warp_bwd_image_rows_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
+        p, static_cast<float*>(workspace));
+    usl::count_launches(1);
+    const long long total = rows * w;
+    blocks = (total + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    usl::warp_bwd_image_blend_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        p, static_cast<const float*>(workspace), grad_image, gi_bs, gi_cs);
+    return usl::check_launch();
+}
 
 extern "C" int usl_warp_fwd(const float* disp, long long disp_bs, float sign,
                             const float* image, long long img_bs,

@@ -378,14 +378,27 @@ def warp_backward_disp(disp: Tensor, sign: float, image: Tensor,
         'usl_warp_bwd_disp')
 
 
+def warp_backward_image(disp: Tensor, sign: float, grad_out: Tensor,
+                        grad_image: Tensor) -> None:
+    b, c, h, w = grad_out.shape
+    nbytes = lib().usl_warp_bwd_image_workspace_bytes(b, c, h, w)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=grad_out.device)
+    check(lib().usl_warp_bwd_image(
+        disp.data_ptr(), disp.stride(0), sign, grad_out.data_ptr(),
+        grad_out.stride(0), grad_out.stride(1), b, c, h, w, ws.data_ptr(),
+        grad_image.data_ptr(), grad_image.stride(0), grad_image.stride(1),
+        _stream(grad_out)), 'usl_warp_bwd_image')
+
+
 class Reconstruct(torch.autograd.Function):
     """train/utils.py:65-109 as one op: out = warp(image; sign * disp).
 
-    Differentiable w.r.t. the disparity (a deterministic gather).  The
-    gradient w.r.t. the sampled image is not provided by this op: on the
-    training path the sampled image is data, and the consistency terms -- the
-    only place the reference differentiates through the sampled map -- are
-    handled inside the fused loss."""
+    Differentiable w.r.t. the disparity (a deterministic gather) and, like the
+    reference's grid_sample, w.r.t. the sampled image (its transpose, also
+    deterministic; not a hot path -- in the training step the sampled image is
+    data, and the consistency terms, the only place the reference
+    differentiates through a sampled map, are handled inside the fused
+    loss)."""
 
     @staticmethod
     def forward(ctx, disp: Tensor, image: Tensor, sign: float) -> Tensor:
@@ -405,16 +418,15 @@ class Reconstruct(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out: Tensor):
         disp, image = ctx.saved_tensors
-        if ctx.needs_input_grad[1]:
-            raise NotImplementedError(
-                'gradient w.r.t. the sampled image of a stand-alone '
-                'reconstruct() is not implemented; use ConsistencyLoss')
-        grad_disp = None
+        grad_out = planes(grad_out)
+        grad_disp = grad_image = None
         if ctx.needs_input_grad[0]:
-            grad_out = planes(grad_out)
             grad_disp = torch.empty_like(disp, memory_format=torch.contiguous_format)
             warp_backward_disp(disp, ctx.sign, image, grad_out, grad_disp)
-        return grad_disp, None, None
+        if ctx.needs_input_grad[1]:
+            grad_image = torch.empty_like(image, memory_format=torch.contiguous_format)
+            warp_backward_image(disp, ctx.sign, grad_out, grad_image)
+        return grad_disp, grad_image, None
 
 
 class ReconstructPair(torch.autograd.Function):
