@@ -512,7 +512,8 @@ def run_ours(args, rank, world, local_rank):
         'e2e': {'value': world * pixels / (m['ms_e2e'] * 1e-3) / 1e6,
                 'unit': UNIT, 'h2d_bytes_per_step': hz.h2d_bytes,
                 'd2h_bytes_per_step': 8, 'ms_per_step': m['ms_e2e'],
-                'h2d_copies_per_step': 1},
+                'h2d_copies_per_step': 1,
+                'host_binding': getattr(args, 'numa', None)},
         # counted (bench.launches_per_step), not assumed
         'gpu_launches': m['launches_per_step'] * args.steps,
         'launches_per_step': m['launches_per_step'],
@@ -753,6 +754,38 @@ def kernel_times(K, hz, dev, reps):
     return out
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run on the CPUs of the NUMA node the GPU hangs off,
+    so that the pinned staging buffers of the end-to-end leg (first touch) lie
+    in that node's memory and the H2D copies do not cross the socket
+    interconnect.  What a launcher would do with `numactl`; torchrun does not.
+    Returns a short description for the JSON line (None if nothing was done)."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id,
+                                    props.pci_device_id)
+        base = f'/sys/bus/pci/devices/{bdf}'
+        with open(f'{base}/numa_node') as f:
+            node = int(f.read().strip())
+        with open(f'{base}/local_cpulist') as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(','):
+            if '-' in part:
+                lo, hi = part.split('-')
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if node < 0 or not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {'numa_node': node, 'cpus': len(cpus)}
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -777,6 +810,7 @@ def main():
         return
     if world > 1:
         import torch.distributed as dist
+        args.numa = bind_to_gpu_numa_node(local_rank)
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda',
                                                                local_rank))
