@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define USL_VERSION 100
+#define USL_VERSION 200
 #define USL_MAX_SCALES 8
 #define USL_NUM_TERMS 6
 

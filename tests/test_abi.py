@@ -38,7 +38,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_version_and_error_strings(lib):
-    assert lib.usl_version() == 100
+    assert lib.usl_version() == 200
     assert lib.usl_strerror(0) == b'ok'
     assert lib.usl_strerror(-1) == b'invalid argument'
     assert lib.usl_strerror(-3) == b'unsupported shape'
