@@ -70,7 +70,7 @@ int main(void) {
     want = [C.sizeof(Cfg), Cfg.coef.offset, C.sizeof(S),
             S.grad_recon_out.offset, S.images.offset, S.err_in.offset,
             S.recon_out.offset, S.grad_disp.offset, _lib.USL_MAX_SCALES,
-            _lib.USL_NUM_TERMS, 100]
+            _lib.USL_NUM_TERMS, 200]
     assert got == want
 
 
