@@ -253,8 +253,11 @@ __device__ __forceinline__ unsigned same_digit_lanes(unsigned d, bool valid) {
 // costs a whole sector of load/store-unit time each).
 // PAYLOAD: 0 = keys only (the oracle curve ranks the pooled map by itself: the
 // value travels inside its key), 1 = values, 2 = values and element indices.
+// (five CTAs per SM: the pass waits on global loads most of the time, 40 warps
+//  hide more of that than the 24 its natural 80 registers allow -- 346 -> ~290
+//  us per pass in spite of ~150 bytes of spills)
 template <int PAYLOAD>
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+__global__ void __launch_bounds__(SORT_THREADS, 5)
 scatter_kernel(const unsigned* __restrict__ keys_in,
                const float* __restrict__ vals_in, const int* __restrict__ idx_in,
                unsigned* __restrict__ keys_out, float* __restrict__ vals_out,
