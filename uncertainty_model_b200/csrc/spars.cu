@@ -286,6 +286,14 @@ scatter_kernel(const unsigned* __restrict__ keys_in,
         const int i = wbase + c * 32 + lane;
         key[c] = i < n ? keys_in[rbase + i] : 0u;
     }
+    if (PAYLOAD) {
+        // the payload is read after the ranking: have it in L2 by then (a line a lane)
+        const int i = wbase + lane * 32;
+        if (lane < SORT_ITEMS && i < n)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vals_in + rbase + i));
+        if (PAYLOAD == 2 && lane < SORT_ITEMS && i < n)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(idx_in + rbase + i));
+    }
 #pragma unroll
     for (int c = 0; c < SORT_ITEMS; ++c) {
         const bool valid = wbase + c * 32 + lane < n;
