@@ -426,7 +426,7 @@ static int launch_scatter(const LossParams* P, int n_scales,
     MultiCons C;
     C.n = 0; C.cta_start[0] = 0; C.skip_if_unit = skip_if_unit;
     size_t csmem = 0;
-    bool use_scat = scat_filled && !knobs().exp[0];
+    bool use_scat = scat_filled && !knobs().scatter_warp_per_row;
     for (int i = 0; i < n_scales; ++i) {
         const LossParams& p = P[i];
         if (only_scale >= 0 && i != only_scale) continue;
@@ -524,7 +524,7 @@ extern "C" int usl_loss_grad(const UslLossConfig* cfgs,
                        (cudaStream_t)stream, &rc, 1, true, 0);
         return rc;
     }
-    if (!(flags & (USL_GRAD_ONLY_SCATTER | USL_GRAD_NO_SCATTER)) && !knobs().exp[1]) {
+    if (!(flags & (USL_GRAD_ONLY_SCATTER | USL_GRAD_NO_SCATTER)) && !knobs().scatter_after_all) {
         // both halves: the scatter of every scale right behind its own fused
         // kernel, on that scale's stream -- the small scales' finish in the
         // shadow of the largest scale's fused kernel
@@ -575,7 +575,7 @@ extern "C" int usl_loss_grad_sharded(const UslLossConfig* cfgs,
     for (int i = 0; i < n_scales; ++i)
         if ((P[i].terms & (TERM_CONS_D | TERM_CONS_U)) && !P[i].scat)
             return USL_ERR_UNSUPPORTED;
-    if (knobs().exp[1]) return USL_ERR_UNSUPPORTED;
+    if (knobs().scatter_after_all) return USL_ERR_UNSUPPORTED;
     AfterScale ctx = {P, n_scales, nullptr, nullptr, 0, 0, (cudaStream_t)reduce_stream};
     if (!try_col(cfgs, scales, n_scales, true, partials, nullptr, nullptr, 0, 0,
                  (cudaStream_t)stream, &rc, scatter_after_scale, &ctx))

@@ -60,7 +60,8 @@ struct Knobs {
     int fwd_tw, fwd_r, bwd_tw, bwd_r;   // USL_{FWD,BWD}_{TW,R}: general kernels
     int cons_r;          // USL_CONS_R
     int scatter_v1;      // USL_SCATTER_V1
-    int exp[8];          // USL_EXP0..7: experiment switches (tuning runs)
+    int scatter_warp_per_row;  // USL_SCATTER_WARP_PER_ROW: round 1's transposed-warp kernel
+    int scatter_after_all;     // USL_SCATTER_AFTER_ALL: one transposed-warp launch behind all column kernels
 };
 inline int knob_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -84,9 +85,8 @@ inline const Knobs& knobs() {
         x.bwd_r = knob_int("USL_BWD_R", 0);
         x.cons_r = knob_int("USL_CONS_R", 0);
         x.scatter_v1 = knob_int("USL_SCATTER_V1", 0);
-        const char* names[8] = {"USL_EXP0", "USL_EXP1", "USL_EXP2", "USL_EXP3",
-                                "USL_EXP4", "USL_EXP5", "USL_EXP6", "USL_EXP7"};
-        for (int i = 0; i < 8; ++i) x.exp[i] = knob_int(names[i], 0);
+        x.scatter_warp_per_row = knob_int("USL_SCATTER_WARP_PER_ROW", 0);
+        x.scatter_after_all = knob_int("USL_SCATTER_AFTER_ALL", 0);
         return x;
     }();
     return k;
