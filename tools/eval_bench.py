@@ -101,7 +101,32 @@ def main():
     t1.record()
     t1.synchronize()
     fms = t0.elapsed_time(t1) / args.reps
+    # the stages of the fused flow (the same calls as evaluate_batch)
+    from uncertainty_model_b200.train import evaluate as E
+    facc = {}
+    for _ in range(args.reps):
+        ev = []
+
+        def fmark(name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e))
+        fmark('start')
+        images = torch.cat([gl, gr], dim=1)
+        recon, error = E.reconstruct_and_error(images, gp)
+        fmark('reconstruct_and_error')
+        E.ssim(recon[:, 0:3], gl, reduction='sum', data_range=1.0)
+        E.ssim(recon[:, 3:6], gr, reduction='sum', data_range=1.0)
+        fmark('ssim_x2')
+        S.curve(error, error, device=dev)
+        S.curve(error, gp[:, 2:4], device=dev)
+        S.curve(error, torch.rand_like(error), device=dev)
+        fmark('three_curves')
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
+            facc[n1] = facc.get(n1, 0.0) + e0.elapsed_time(e1)
     out['fused'] = {'ms': round(fms, 3),
+                    'stage_ms': {k: round(v / args.reps, 3) for k, v in facc.items()},
                     'frames_per_s': round(args.frames / (fms * 1e-3), 1),
                     'includes': 'SSIM metric of both views',
                     'ause': float(fa[0]), 'left_ssim': float(fa[2]),
